@@ -1,0 +1,150 @@
+/*
+ * toygpu.h -- C ABI of libtoygpu.so, the B200 (sm_100a) replacement for Toycluster's
+ * SPH-density + WVT-relaxation hot path.
+ *
+ * The reference has no plugin/FFI layer: its de-facto operator API is three global-state
+ * procedures called from main() (main.c:52-56):
+ *
+ *     void Regularise_sph_particles();   wvt_relax.c:25
+ *     void Find_sph_quantities();        sph.c:13
+ *     void Bfld_from_rotA_SPH();         sph.c:216
+ *
+ * toycluster_b200/host/gpu_shim.c defines exactly those three symbols on top of the entry
+ * points below.  Every function returns 0 on success and a negative
+ * TG_E* code on failure; tg_last_error() gives the message.  All pointers are caller-owned
+ * HOST memory unless a name says "dev"; the context owns all device memory.  One caller
+ * thread per context, as in the reference (global state, non-reentrant).
+ */
+#ifndef TOYGPU_H
+#define TOYGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_DESNNGB 295   /* globals.h:48 */
+#define TG_NGBMAX  2360  /* globals.h:50 */
+#define TG_NUMITER 64    /* wvt_relax.c:7 */
+
+enum {
+    TG_OK = 0,
+    TG_EINVAL = -1,    /* bad argument / call order */
+    TG_ECUDA = -2,     /* CUDA runtime error */
+    TG_ENOMEM = -3,
+    TG_ENOCONV = -4,   /* hsml iteration did not terminate (sph.c:36-64 would spin) */
+    TG_ERANGE = -5     /* position outside [0, Boxsize] (peano.c:130-132 asserts) */
+};
+
+/* tg_config.flags */
+#define TG_WVT_SEQUENTIAL 1u  /* accumulate the displacement in the reference's order and
+                                 precision (float += double, ascending neighbour index,
+                                 wvt_relax.c:167-169) instead of one FP64 tree sum */
+
+/* One row of the table Global_density_model() walks (wvt_relax.c:227-256):
+ * Halo[i].{D_CoM, Rho0, Beta, Rcore, Rcut, Have_Cuspy, Mass[0]} (globals.h:128-157). */
+typedef struct {
+    double dcom[3];
+    double rho0, beta, rcore, rcut;
+    int cuspy;
+    double mass_gas;
+} tg_halo;
+
+typedef struct {
+    int device;          /* CUDA device ordinal */
+    int n_gas;           /* Param.Npart[0] */
+    double boxsize;      /* Param.Boxsize */
+    double mpart_gas;    /* Param.Mpart[0] */
+    double mtotal;       /* Param.Mtotal (wvt_relax.c:53) */
+    unsigned flags;
+    int rank, nranks;    /* target-particle partition; 0,1 for one GPU */
+} tg_config;
+
+typedef struct tg_ctx tg_ctx;
+
+/* Per-iteration observer == the printf at wvt_relax.c:91-92. Return non-zero to stop. */
+typedef int (*tg_log_fn)(int it, double err_max, double err_mean, double err_diff,
+                         double step, void *user);
+
+/* Counters of the last tg_find_sph_quantities / WVT iteration (bench.py's metric). */
+typedef struct {
+    unsigned long long pair_evals;   /* sum over Find_hsml iterations of list length
+                                        + WVT pairs (reference semantics) */
+    unsigned long long gathered;     /* G_step: distinct neighbours gathered */
+    unsigned long long searches;     /* neighbour searches (tree.c:25 equivalents) */
+    unsigned long long hsml_iters;   /* Find_hsml inner iterations (sph.c:96) */
+    unsigned long long kernels;      /* kernel launches */
+    double sweep_ms;                 /* device time of the neighbour sweep kernel(s) */
+    double step_ms;                  /* device time of the whole step */
+} tg_stats;
+
+/* ---- life cycle -------------------------------------------------------------------- */
+int tg_create(tg_ctx **out, const tg_config *cfg);
+int tg_destroy(tg_ctx *ctx);
+const char *tg_last_error(const tg_ctx *ctx);    /* ctx may be NULL (last create error) */
+
+/* Halo table for Global_density_model (replaces reading Halo[] / Param.Nhalos). */
+int tg_set_halos(tg_ctx *ctx, int n, const tg_halo *halos);
+
+/* ---- data in / out ----------------------------------------------------------------- */
+/* AoS records exactly as the driver holds them: struct ParticleData (globals.h:161-168,
+ * Pos at +0) and struct GasParticleData (globals.h:170-180, Hsml at +8, Apot at +28).
+ * Only the gas range [0, n_gas) is read. */
+int tg_upload(tg_ctx *ctx, const void *P, size_t p_stride, const void *SphP, size_t s_stride);
+/* Same from plain arrays: pos[n][3]; hsml[n] or NULL (cold start, SphP.Hsml == 0). */
+int tg_upload_soa(tg_ctx *ctx, const float *pos, const float *hsml);
+int tg_set_apot(tg_ctx *ctx, const float *apot /* [n][3], upload order */);
+
+/* Writes the path's post-state back into the driver's records: the gas range of P and
+ * SphP permuted into the Peano order of the last density call (peano.c:85-126 moves whole
+ * records), with Pos, Key, Tree_Parent, Hsml, Rho, VarHsmlFac, Rho_Model, Bfld updated. */
+int tg_download(tg_ctx *ctx, void *P, size_t p_stride, void *SphP, size_t s_stride);
+/* SoA read-back in the current (Peano) order; any pointer may be NULL.
+ * perm[k] = upload index of the particle now at k. */
+int tg_download_soa(tg_ctx *ctx, float *pos, int32_t *perm, float *hsml, float *rho,
+                    float *varhsml, float *rho_model, float *bfld);
+
+/* ---- the three operators ----------------------------------------------------------- */
+int tg_find_sph_quantities(tg_ctx *ctx);                       /* == sph.c:13       */
+int tg_regularise(tg_ctx *ctx, int max_iters, tg_log_fn log, void *user,
+                  int *iters_done);                            /* == wvt_relax.c:25 */
+int tg_bfld_from_rotA(tg_ctx *ctx);                            /* == sph.c:216      */
+
+/* One pass of wvt_relax.c:66-214 with the step given by the caller (bench.py's "step",
+ * and the per-iteration parity tests).  Runs sort + index + density + error + model hsml +
+ * displacement + move; err_max/err_mean as at wvt_relax.c:73-87. */
+int tg_wvt_iteration(tg_ctx *ctx, double step, double *err_max, double *err_mean);
+/* Scratch of the last iteration (wvt_relax.c:36-44), in that iteration's Peano order. */
+int tg_wvt_scratch(tg_ctx *ctx, float *hsml_wvt, float *delta /* [n][3] */);
+
+int tg_get_stats(tg_ctx *ctx, tg_stats *out);
+
+/* ---- test hooks (parity with peano.c / sort.c / tree.c) ----------------------------- */
+/* Peano_Key of every uploaded particle, upload order (peano.c:63-71). */
+int tg_peano_keys(tg_ctx *ctx, uint64_t *hi, uint64_t *lo);
+/* Key build + sort + reorder only (peano.c:46-81); perm as in tg_download_soa. */
+int tg_sort(tg_ctx *ctx, int32_t *perm);
+/* Find_ngb_tree(i, h) on the current index (tree.c:25): ascending, at most TG_NGBMAX. */
+int tg_find_ngb(tg_ctx *ctx, int i, float h, int32_t *list, int *count);
+/* 2*Guess_hsml(i) for every particle of the current order (tree.c:113, sph.c:26). */
+int tg_guess_hsml(tg_ctx *ctx, float *out);
+
+/* ---- multi-GPU plumbing (one process per GPU) ---------------------------- */
+/* Device pointers of the arrays a rank must exchange after computing its slice
+ * [lo, hi) of targets; the host does the all-gather (NCCL via torch.distributed). */
+typedef struct {
+    void *pos_hsml_dev;   /* float4[n]: x, y, z, Hsml of the current order */
+    void *rho_dev;        /* float[n]  */
+    void *varhsml_dev;    /* float[n]  */
+    void *delta_dev;      /* float[3][n] */
+    void *err_dev;        /* double[2]: sum err, max err of the local slice */
+    int lo, hi;
+} tg_exchange;
+int tg_get_exchange(tg_ctx *ctx, tg_exchange *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOYGPU_H */

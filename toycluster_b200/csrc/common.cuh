@@ -1,0 +1,63 @@
+// common.cuh -- shared device helpers and the parameter block every kernel receives.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define TG_DESNNGB 295
+#define TG_NGBMAX 2360
+#define FULL_MASK 0xffffffffu
+#define MAX_LEVELS 8
+#define MAX_HALOS 128
+
+// globals.h:62-63 -- the reference's literal constants, not the exact values
+#define K_SQRT3 1.73205080756887719
+#define K_FOURPITHIRD 4.18879032135009765
+#define K_PI 3.14159265358979323846
+
+struct Halo {            // one row of Global_density_model's table
+    double cx, cy, cz;   // D_CoM; Boxsize/2 is subtracted at evaluation time (wvt_relax.c:240)
+    double rho0, beta, rcore, rcut;
+    double mass_gas;
+};
+
+// Sorted-order bounding-box hierarchy over groups of 32 consecutive particles.
+// Level 0 = groups of 32 particles, level l+1 = groups of 32 level-l nodes.
+struct Bvh {
+    int n;                    // particles
+    int top;                  // highest level; it has <= 32 nodes
+    int lvl_n[MAX_LEVELS];    // nodes per level
+    int lvl_off[MAX_LEVELS];  // offset of each level in the SoA arrays
+    const float *cx, *cy, *cz;   // box centres
+    const float *hx, *hy, *hz;   // box half-widths (already inflated for rounding)
+};
+
+struct Box {
+    float box_f, boxhalf_f;             // tree.c:27-28
+    double box_d, boxhalf_d, boxinv_d;  // sph.c:83-84, wvt_relax.c:28-29
+    double mpart;                       // Param.Mpart[0]
+};
+
+static __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+static __device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;   // xor butterfly: every lane ends with the bit-identical total
+}
+
+static __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+// Correctly rounded float ops without FMA contraction: the reference is built -std=c99,
+// i.e. -ffp-contract=off, so tree.c:88 is three rounded products and two rounded sums.
+static __device__ __forceinline__ float sq3_nofma(float a, float b, float c)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c));
+}

@@ -1,0 +1,175 @@
+// radix.cuh -- stable LSD radix sort of (64-bit key, 32-bit index), replacing the serial
+// gsl_heapsort_index of sort.c:189-195 (the 240-line OpenMP quicksort below it is dead code).
+//
+// Sorting the upper 64 bits of the 128-bit Peano key (21 triplets + 1 bit: 2^-21 Boxsize
+// per axis) orders all but pathologically close particles; k_fix_ties then orders every run
+// of equal upper halves by the lower half, and equal 128-bit keys (bit-identical positions,
+// which the reference's unstable heapsort leaves in heap order) by upload index.
+//
+// Each pass is three kernels over tiles of RS_TILE keys:
+//   k_radix_hist    per-tile digit histogram -> hist[digit][tile]
+//   k_radix_scan    exclusive scan of hist in digit-major order (one block)
+//   k_radix_scatter stable rank of every key inside its tile (warp match + per-warp counters)
+//                   and scatter to hist[digit][tile] + rank
+#pragma once
+#include "common.cuh"
+
+#define RS_BITS 8
+#define RS_BINS 256
+#define RS_THREADS 256
+#define RS_WARPS (RS_THREADS / 32)
+#define RS_ITEMS 8                       // keys per thread
+#define RS_TILE (RS_THREADS * RS_ITEMS)  // 2048 keys per block
+#define RS_WARP_SEG (32 * RS_ITEMS)      // consecutive keys owned by one warp
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_hist(int n, const uint64_t *__restrict__ keys, int shift, int ntiles,
+             unsigned *__restrict__ hist)
+{
+    __shared__ unsigned bins[RS_BINS];
+    for (int b = threadIdx.x; b < RS_BINS; b += RS_THREADS) bins[b] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int k = base + it * RS_THREADS + threadIdx.x;
+        if (k < n) atomicAdd(&bins[(keys[k] >> shift) & (RS_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < RS_BINS; b += RS_THREADS)
+        hist[(size_t)b * ntiles + blockIdx.x] = bins[b];
+}
+
+// Exclusive scan of `count` unsigned values, in place, by one block of 1024 threads.
+__global__ void __launch_bounds__(1024) k_radix_scan(size_t count, unsigned *__restrict__ data)
+{
+    __shared__ unsigned warp_tot[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (size_t base = 0; base < count; base += 1024 * 4) {
+        // each thread owns 4 consecutive values
+        const size_t k0 = base + (size_t)threadIdx.x * 4;
+        unsigned v[4], s = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { v[j] = (k0 + j < count) ? data[k0 + j] : 0u; s += v[j]; }
+        unsigned incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            unsigned t = warp_tot[lane], i2 = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned u = __shfl_up_sync(FULL_MASK, i2, o);
+                if (lane >= o) i2 += u;
+            }
+            warp_tot[lane] = i2 - t;   // exclusive over warps
+        }
+        __syncthreads();
+        unsigned excl = carry + warp_tot[w] + incl - s;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (k0 + j < count) data[k0 + j] = excl;
+            excl += v[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_scatter(int n, const uint64_t *__restrict__ keys_in, const int *__restrict__ idx_in,
+                uint64_t *__restrict__ keys_out, int *__restrict__ idx_out, int shift,
+                int ntiles, const unsigned *__restrict__ hist)
+{
+    __shared__ unsigned cnt[RS_WARPS][RS_BINS];   // per-warp digit counters -> warp offsets
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int b = threadIdx.x; b < RS_WARPS * RS_BINS; b += RS_THREADS) (&cnt[0][0])[b] = 0;
+    __syncthreads();
+
+    // Warp w owns keys [base + w*RS_WARP_SEG, +RS_WARP_SEG) in rounds of 32: tile order ==
+    // (warp, round, lane) order, so ranks assigned in that order are stable.
+    const int base = blockIdx.x * RS_TILE + w * RS_WARP_SEG;
+    uint64_t key[RS_ITEMS];
+    int val[RS_ITEMS];
+    unsigned rank[RS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int k = base + it * 32 + lane;
+        const bool live = k < n;
+        key[it] = live ? keys_in[k] : ~0ull;
+        val[it] = live ? idx_in[k] : 0;
+        const unsigned d = (unsigned)(key[it] >> shift) & (RS_BINS - 1);
+        // lanes with the same digit (dead lanes form their own group and touch nothing)
+        unsigned peers = __match_any_sync(FULL_MASK, live ? d : 0x10000u);
+        const unsigned before = __popc(peers & ((1u << lane) - 1));
+        const int leader = __ffs(peers) - 1;
+        unsigned start = 0;
+        if (live && lane == leader) {
+            start = cnt[w][d];
+            cnt[w][d] = start + __popc(peers);
+        }
+        start = __shfl_sync(FULL_MASK, start, leader);
+        rank[it] = start + before;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // exclusive prefix over warps for every digit, plus the tile's global offset
+    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) {
+        unsigned run = hist[(size_t)d * ntiles + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) {
+            unsigned c = cnt[ww][d];
+            cnt[ww][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int k = base + it * 32 + lane;
+        if (k < n) {
+            const unsigned d = (unsigned)(key[it] >> shift) & (RS_BINS - 1);
+            const unsigned dst = cnt[w][d] + rank[it];
+            keys_out[dst] = key[it];
+            idx_out[dst] = val[it];
+        }
+    }
+}
+
+// After the 64-bit sort: order runs of equal key_hi by (key_lo, index). One thread per run
+// start; runs are a handful of particles at most, so a serial insertion sort is fine.
+__global__ void k_fix_ties(int n, const uint64_t *__restrict__ hi_sorted, int *__restrict__ idx,
+                           const uint64_t *__restrict__ key_lo, int *__restrict__ n_tied)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint64_t h = hi_sorted[k];
+    if (k > 0 && hi_sorted[k - 1] == h) return;      // not a run start
+    if (k + 1 >= n || hi_sorted[k + 1] != h) return;  // run of one
+    int end = k + 1;
+    while (end < n && hi_sorted[end] == h) end++;
+    atomicAdd(n_tied, end - k);
+    for (int a = k + 1; a < end; a++) {
+        const int ia = idx[a];
+        const uint64_t la = key_lo[ia];
+        int b = a - 1;
+        while (b >= k) {
+            const int ib = idx[b];
+            const uint64_t lb = key_lo[ib];
+            if (lb < la || (lb == la && ib < ia)) break;
+            idx[b + 1] = ib;
+            b--;
+        }
+        idx[b + 1] = ia;
+    }
+}

@@ -1,0 +1,847 @@
+// toygpu.cu -- context, step orchestration and the C ABI of include/toygpu.h.
+//
+// Data layout in HBM (all SoA, n = gas particles):
+//   state   posh  float4[n]  (x, y, z, Hsml) of the current order       16 B
+//           id    int[n]     upload index of the particle               4 B
+//   sort    key_hi/key_lo u64[n], idx int[n] (+ ping-pong copies)
+//   sorted  pw    float4[n]  (x, y, z, raw WVT hsml) -- the one array the sweep gathers
+//           hsml_in, rho_model float[n], key_hi_s/key_lo_s u64[n]
+//   result  hsml_out, rho, varhsml float[n], delta float[3][n], bfld float[n][3]
+//   index   6 float arrays of ~n/31 boxes
+// About 150 B per particle: 1.5 GB at 10 M, far inside 180 GB.
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/toygpu.h"
+#include "common.cuh"
+#include "peano.cuh"
+#include "radix.cuh"
+#include "bvh.cuh"
+#include "model.cuh"
+#include "guess.cuh"
+#include "sph.cuh"
+
+static thread_local std::string g_create_error;
+
+struct tg_ctx {
+    tg_config cfg{};
+    std::string err;
+    cudaStream_t stream = nullptr;
+    int n = 0, lo = 0, hi = 0;
+    Box box{};
+    double bias_const = 0;
+
+    // state (current order)
+    float4 *posh = nullptr;
+    int *id = nullptr;
+    float *apot = nullptr;          // [n][3] or null
+    bool have_apot = false;
+    bool any_cold = true;
+    bool index_valid = false;
+
+    // sort
+    uint64_t *key_hi = nullptr, *key_lo = nullptr, *key_tmp = nullptr;
+    int *idx = nullptr, *idx_tmp = nullptr;
+    unsigned *hist = nullptr;
+    int ntiles = 0;
+    uint64_t *key_hi_s = nullptr;   // points at key_hi or key_tmp after the last pass
+    int *idx_s = nullptr;
+
+    // sorted
+    float4 *pw = nullptr;
+    float *hsml_in = nullptr, *rho_model = nullptr;
+    int *id_s = nullptr;
+    uint64_t *key_lo_s = nullptr;
+    float *apot_s = nullptr;
+
+    // results
+    float *hsml_out = nullptr, *rho = nullptr, *varh = nullptr, *delta = nullptr, *bfld = nullptr;
+
+    // index
+    Bvh bvh{};
+    float *bvh_mem = nullptr;
+    int bvh_total = 0;
+
+    // cold start
+    signed char *cpl = nullptr, *ev_level = nullptr, *ev_count = nullptr;
+    int *ev_start = nullptr;
+    float *guess = nullptr;
+
+    // scalars / scratch
+    Halo *halos = nullptr;
+    int nhalos = 0;
+    double *partial = nullptr;      // block partials
+    int npartial = 0;
+    double *scal = nullptr;         // [0] vsum, [1] err sum, [2] err max
+    int *flags = nullptr;           // [0] next, [1] status, [2] range_err, [3] n_tied
+    unsigned long long *counters = nullptr;   // 4
+    double *gscratch = nullptr;
+    int sweep_blocks = 0;
+
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    tg_stats stats{};
+    unsigned long long launches = 0;
+};
+
+static int fail(tg_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess)                                                        \
+            return fail(c, TG_ECUDA, "%s failed: %s (%s:%d)", #call,                  \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                  \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                \
+    do {                                                                              \
+        c->launches++;                                                                \
+        cudaError_t e_ = cudaGetLastError();                                          \
+        if (e_ != cudaSuccess)                                                        \
+            return fail(c, TG_ECUDA, "kernel launch failed: %s (%s:%d)",              \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                  \
+    } while (0)
+
+template <class T> static cudaError_t dmalloc(T **p, size_t count)
+{
+    return cudaMalloc((void **)p, (count ? count : 1) * sizeof(T));
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------ life cycle
+
+extern "C" const char *tg_last_error(const tg_ctx *c)
+{
+    return c ? c->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int tg_destroy(tg_ctx *c)
+{
+    if (!c) return TG_OK;
+    cudaSetDevice(c->cfg.device);
+    void *ptrs[] = {c->posh, c->id, c->apot, c->key_hi, c->key_lo, c->key_tmp, c->idx, c->idx_tmp,
+                    c->hist, c->pw, c->hsml_in, c->rho_model, c->id_s, c->key_lo_s, c->apot_s,
+                    c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->cpl,
+                    c->ev_level, c->ev_count, c->ev_start, c->guess, c->halos, c->partial, c->scal,
+                    c->flags, c->counters, c->gscratch};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return TG_OK;
+}
+
+extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
+{
+    tg_ctx *c = nullptr;
+    if (!out || !cfg) return fail(c, TG_EINVAL, "tg_create: null argument");
+    *out = nullptr;
+    if (cfg->n_gas <= 0 || !(cfg->boxsize > 0) || !(cfg->mpart_gas > 0))
+        return fail(c, TG_EINVAL, "tg_create: n_gas, boxsize and mpart_gas must be positive");
+    const int nranks = cfg->nranks > 0 ? cfg->nranks : 1;
+    if (cfg->rank < 0 || cfg->rank >= nranks)
+        return fail(c, TG_EINVAL, "tg_create: rank %d outside [0,%d)", cfg->rank, nranks);
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(c, TG_ECUDA, "tg_create: no CUDA device (%s); libtoygpu has no CPU path",
+                    cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(c, TG_EINVAL, "tg_create: device %d of %d", cfg->device, ndev);
+
+    tg_ctx *ctx = new tg_ctx;
+    c = ctx;
+    c->cfg = *cfg;
+    c->cfg.nranks = nranks;
+    const int n = c->n = cfg->n_gas;
+    c->lo = (int)((long long)n * cfg->rank / nranks);
+    c->hi = (int)((long long)n * (cfg->rank + 1) / nranks);
+
+    c->box.box_d = cfg->boxsize;
+    c->box.boxhalf_d = 0.5 * cfg->boxsize;            // sph.c:83
+    c->box.boxinv_d = 1 / cfg->boxsize;               // wvt_relax.c:29
+    c->box.box_f = (float)cfg->boxsize;               // tree.c:27
+    c->box.boxhalf_f = (float)(cfg->boxsize * 0.5);   // tree.c:28
+    c->box.mpart = cfg->mpart_gas;
+    c->bias_const = -0.0116 * pow(TG_DESNNGB * 0.01, -2.236);   // sph.c:206, host libm
+
+#define CUC(call)                                                                     \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            fail(nullptr, TG_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_));  \
+            tg_destroy(ctx);                                                          \
+            return e_ == cudaErrorMemoryAllocation ? TG_ENOMEM : TG_ECUDA;            \
+        }                                                                             \
+    } while (0)
+
+    CUC(cudaSetDevice(cfg->device));
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &ev : c->ev) CUC(cudaEventCreate(&ev));
+
+    CUC(dmalloc(&c->posh, n));
+    CUC(dmalloc(&c->id, n));
+    CUC(dmalloc(&c->key_hi, n));
+    CUC(dmalloc(&c->key_lo, n));
+    CUC(dmalloc(&c->key_tmp, n));
+    CUC(dmalloc(&c->idx, n));
+    CUC(dmalloc(&c->idx_tmp, n));
+    c->ntiles = cdiv(n, RS_TILE);
+    CUC(dmalloc(&c->hist, (size_t)RS_BINS * c->ntiles));
+    CUC(dmalloc(&c->pw, n));
+    CUC(dmalloc(&c->hsml_in, n));
+    CUC(dmalloc(&c->rho_model, n));
+    CUC(dmalloc(&c->id_s, n));
+    CUC(dmalloc(&c->key_lo_s, n));
+    CUC(dmalloc(&c->hsml_out, n));
+    CUC(dmalloc(&c->rho, n));
+    CUC(dmalloc(&c->varh, n));
+    CUC(dmalloc(&c->delta, (size_t)3 * n));
+    CUC(dmalloc(&c->bfld, (size_t)3 * n));
+    CUC(cudaMemsetAsync(c->rho, 0, sizeof(float) * n, c->stream));
+    CUC(cudaMemsetAsync(c->varh, 0, sizeof(float) * n, c->stream));
+    CUC(cudaMemsetAsync(c->rho_model, 0, sizeof(float) * n, c->stream));
+    CUC(cudaMemsetAsync(c->delta, 0, sizeof(float) * 3 * n, c->stream));
+    CUC(cudaMemsetAsync(c->bfld, 0, sizeof(float) * 3 * n, c->stream));
+
+    // index levels
+    Bvh &t = c->bvh;
+    t.n = n;
+    int cnt = cdiv(n, 32), lvl = 0, total = 0;
+    for (;;) {
+        if (lvl >= MAX_LEVELS) { tg_destroy(ctx); return fail(nullptr, TG_EINVAL, "too many index levels"); }
+        t.lvl_n[lvl] = cnt;
+        t.lvl_off[lvl] = total;
+        total += cnt;
+        if (cnt <= 32) break;
+        cnt = cdiv(cnt, 32);
+        lvl++;
+    }
+    t.top = lvl;
+    c->bvh_total = total;
+    CUC(dmalloc(&c->bvh_mem, (size_t)6 * total));
+    t.cx = c->bvh_mem; t.cy = c->bvh_mem + total; t.cz = c->bvh_mem + 2 * (size_t)total;
+    t.hx = c->bvh_mem + 3 * (size_t)total; t.hy = c->bvh_mem + 4 * (size_t)total;
+    t.hz = c->bvh_mem + 5 * (size_t)total;
+
+    CUC(dmalloc(&c->cpl, n));
+    CUC(dmalloc(&c->ev_level, n));
+    CUC(dmalloc(&c->ev_count, n));
+    CUC(dmalloc(&c->ev_start, n));
+    CUC(dmalloc(&c->guess, n));
+
+    CUC(dmalloc(&c->halos, MAX_HALOS));
+    c->npartial = cdiv(n, RED_THREADS);
+    CUC(dmalloc(&c->partial, (size_t)2 * c->npartial));
+    CUC(dmalloc(&c->scal, 4));
+    CUC(dmalloc(&c->flags, 4));
+    CUC(dmalloc(&c->counters, 4));
+    CUC(cudaMemsetAsync(c->flags, 0, 4 * sizeof(int), c->stream));
+    CUC(cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned long long), c->stream));
+
+    // sweep grid: every SM full of resident blocks (persistent, work-stealing)
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, cfg->device));
+    const size_t smem = (size_t)SW_WARPS * SW_LCAP * sizeof(double);
+    int per_sm = 1;
+    {
+        auto set = [&](const void *f) {
+            return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        };
+        CUC(set((const void *)k_sweep<MODE_DENSITY>));
+        CUC(set((const void *)k_sweep<MODE_WVT>));
+        CUC(set((const void *)k_sweep<MODE_WVT_SEQ>));
+        CUC(set((const void *)k_sweep<MODE_DENSITY | MODE_WVT>));
+        CUC(set((const void *)k_sweep<MODE_ROTA>));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep<MODE_DENSITY | MODE_WVT>,
+                                                          SW_WARPS * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
+    c->sweep_blocks = prop.multiProcessorCount * per_sm;
+    CUC(dmalloc(&c->gscratch, (size_t)c->sweep_blocks * SW_WARPS * TG_NGBMAX));
+    CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+    *out = ctx;
+    return TG_OK;
+}
+
+extern "C" int tg_set_halos(tg_ctx *c, int n, const tg_halo *h)
+{
+    if (!c || n < 0 || n > MAX_HALOS || (n && !h)) return fail(c, TG_EINVAL, "tg_set_halos: bad arguments (max %d rows)", MAX_HALOS);
+    CU(cudaSetDevice(c->cfg.device));
+    std::vector<Halo> rows(n);
+    for (int i = 0; i < n; i++) {
+        rows[i].cx = h[i].dcom[0]; rows[i].cy = h[i].dcom[1]; rows[i].cz = h[i].dcom[2];
+        rows[i].rho0 = h[i].rho0; rows[i].beta = h[i].beta;
+        rows[i].rcore = h[i].rcore; rows[i].rcut = h[i].rcut;
+        rows[i].mass_gas = h[i].mass_gas;
+    }
+    if (n) CU(cudaMemcpyAsync(c->halos, rows.data(), n * sizeof(Halo), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->nhalos = n;
+    return TG_OK;
+}
+
+// ------------------------------------------------------------------ data in
+
+static int upload_common(tg_ctx *c, const std::vector<float4> &posh)
+{
+    const int n = c->n;
+    CU(cudaSetDevice(c->cfg.device));
+    std::vector<int> ids(n);
+    bool cold = false;
+    for (int i = 0; i < n; i++) { ids[i] = i; cold |= posh[i].w == 0; }
+    CU(cudaMemcpyAsync(c->posh, posh.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->id, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->any_cold = cold;
+    c->index_valid = false;
+    c->have_apot = false;
+    return TG_OK;
+}
+
+extern "C" int tg_upload_soa(tg_ctx *c, const float *pos, const float *hsml)
+{
+    if (!c || !pos) return fail(c, TG_EINVAL, "tg_upload_soa: null argument");
+    std::vector<float4> posh(c->n);
+    for (int i = 0; i < c->n; i++)
+        posh[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], hsml ? hsml[i] : 0.f);
+    return upload_common(c, posh);
+}
+
+extern "C" int tg_upload(tg_ctx *c, const void *P, size_t p_stride, const void *SphP, size_t s_stride)
+{
+    if (!c || !P || !SphP || p_stride < 12 || s_stride < 12)
+        return fail(c, TG_EINVAL, "tg_upload: bad arguments");
+    std::vector<float4> posh(c->n);
+    std::vector<float> apot((size_t)3 * c->n);
+    const bool with_apot = s_stride >= 40;
+    for (int i = 0; i < c->n; i++) {
+        const float *pos = (const float *)((const char *)P + i * p_stride);            // Pos @ +0
+        const float *sph = (const float *)((const char *)SphP + i * s_stride);
+        posh[i] = make_float4(pos[0], pos[1], pos[2], sph[2]);                          // Hsml @ +8
+        if (with_apot) for (int k = 0; k < 3; k++) apot[3 * (size_t)i + k] = sph[7 + k];   // Apot @ +28
+    }
+    int rc = upload_common(c, posh);
+    if (rc == TG_OK && with_apot) rc = tg_set_apot(c, apot.data());
+    return rc;
+}
+
+// apot is given in the CURRENT order of the context (upload order right after an upload,
+// Peano order after a density call -- the order tg_download_soa reports).
+extern "C" int tg_set_apot(tg_ctx *c, const float *apot)
+{
+    if (!c || !apot) return fail(c, TG_EINVAL, "tg_set_apot: null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    if (!c->apot) {
+        CU(dmalloc(&c->apot, (size_t)3 * c->n));
+        CU(dmalloc(&c->apot_s, (size_t)3 * c->n));
+    }
+    CU(cudaMemcpyAsync(c->apot, apot, sizeof(float) * 3 * c->n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_apot = true;
+    return TG_OK;
+}
+
+// ------------------------------------------------------------------ step pieces
+
+static int reset_counters(tg_ctx *c)
+{
+    CU(cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    CU(cudaMemsetAsync(c->flags + 1, 0, sizeof(int), c->stream));   // sweep status
+    c->launches = 0;
+    return TG_OK;
+}
+
+// peano.c:46-81 (keys, index sort) -- leaves key_hi_s / idx_s.
+static int sort_keys(tg_ctx *c)
+{
+    const int n = c->n, T = 256;
+    CU(cudaMemsetAsync(c->flags + 2, 0, 2 * sizeof(int), c->stream));
+    k_peano_keys<<<cdiv(n, T), T, 0, c->stream>>>(n, c->posh, c->box.box_d, c->key_hi, c->key_lo,
+                                                 c->idx, c->flags + 2);
+    LAUNCH_CHECK();
+    uint64_t *kin = c->key_hi, *kout = c->key_tmp;
+    int *iin = c->idx, *iout = c->idx_tmp;
+    for (int shift = 0; shift < 64; shift += RS_BITS) {
+        k_radix_hist<<<c->ntiles, RS_THREADS, 0, c->stream>>>(n, kin, shift, c->ntiles, c->hist);
+        LAUNCH_CHECK();
+        k_radix_scan<<<1, 1024, 0, c->stream>>>((size_t)RS_BINS * c->ntiles, c->hist);
+        LAUNCH_CHECK();
+        k_radix_scatter<<<c->ntiles, RS_THREADS, 0, c->stream>>>(n, kin, iin, kout, iout, shift,
+                                                                c->ntiles, c->hist);
+        LAUNCH_CHECK();
+        std::swap(kin, kout);
+        std::swap(iin, iout);
+    }
+    c->key_hi_s = kin;
+    c->idx_s = iin;
+    k_fix_ties<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->idx_s, c->key_lo, c->flags + 3);
+    LAUNCH_CHECK();
+    return TG_OK;
+}
+
+// Sort_Particles_By_Peano_Key + Build_Tree equivalents, plus the position-only model pass.
+static int prepare_index(tg_ctx *c)
+{
+    const int n = c->n, T = 256;
+    if (c->nhalos == 0) return fail(c, TG_EINVAL, "tg_set_halos has not been called");
+    int rc = sort_keys(c);
+    if (rc) return rc;
+
+    k_reorder_model<<<c->npartial, RED_THREADS, 0, c->stream>>>(
+        n, c->idx_s, c->posh, c->id, c->key_lo, c->have_apot ? c->apot : nullptr, c->pw, c->hsml_in,
+        c->id_s, c->rho_model, c->key_lo_s, c->apot_s, c->halos, c->nhalos, c->box.mpart,
+        c->box.boxhalf_d, c->partial);
+    LAUNCH_CHECK();
+    k_final_sum<<<1, RED_THREADS, 0, c->stream>>>(c->npartial, c->partial, c->scal);
+    LAUNCH_CHECK();
+
+    const Bvh &t = c->bvh;
+    float *m = c->bvh_mem;
+    const size_t S = c->bvh_total;
+    const float pad = 4e-7f * c->box.box_f;
+    k_bvh_leaves<<<cdiv((long long)t.lvl_n[0] * 32, T), T, 0, c->stream>>>(
+        n, c->pw, t.lvl_n[0], pad, m, m + S, m + 2 * S, m + 3 * S, m + 4 * S, m + 5 * S);
+    LAUNCH_CHECK();
+    for (int l = 1; l <= t.top; l++) {
+        const int oc = t.lvl_off[l - 1], op = t.lvl_off[l];
+        k_bvh_up<<<cdiv((long long)t.lvl_n[l] * 32, T), T, 0, c->stream>>>(
+            t.lvl_n[l - 1], t.lvl_n[l], pad, m + oc, m + S + oc, m + 2 * S + oc, m + 3 * S + oc,
+            m + 4 * S + oc, m + 5 * S + oc, m + op, m + S + op, m + 2 * S + op, m + 3 * S + op,
+            m + 4 * S + op, m + 5 * S + op);
+        LAUNCH_CHECK();
+    }
+
+    if (c->any_cold) {   // tree.c:113-121 stand-in for particles with Hsml == 0
+        k_cpl<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->key_lo_s, c->cpl);
+        LAUNCH_CHECK();
+        k_collapse_events<<<cdiv(n, T), T, 0, c->stream>>>(n, c->cpl, c->ev_start, c->ev_level, c->ev_count);
+        LAUNCH_CHECK();
+        k_guess_hsml<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->key_lo_s, c->cpl, c->ev_start,
+                                                     c->ev_level, c->ev_count, c->box.box_d, c->guess,
+                                                     nullptr);
+        LAUNCH_CHECK();
+    }
+
+    // the sorted order is now the current order
+    std::swap(c->id, c->id_s);
+    if (c->have_apot) std::swap(c->apot, c->apot_s);
+    c->index_valid = true;
+    return TG_OK;
+}
+
+static SweepArgs sweep_args(tg_ctx *c, double step)
+{
+    SweepArgs a{};
+    a.t = c->bvh;
+    a.bx = c->box;
+    a.pw = c->pw;
+    a.hsml_in = c->hsml_in;
+    a.guess = c->guess;
+    a.hsml_out = c->hsml_out;
+    a.rho_out = c->rho;
+    a.varh_out = c->varh;
+    a.delta = c->delta;
+    a.vsum = c->scal;
+    a.step = step;
+    a.bias_const = c->bias_const;
+    a.lo = c->lo;
+    a.hi = c->hi;
+    a.next = c->flags;
+    a.gscratch = c->gscratch;
+    a.counters = c->counters;
+    a.status = c->flags + 1;
+    a.rho_in = c->rho;
+    a.varh_in = c->varh;
+    a.apot = c->apot;
+    a.bfld = c->bfld;
+    return a;
+}
+
+template <int MODE> static int launch_sweep(tg_ctx *c, const SweepArgs &a)
+{
+    const size_t smem = (size_t)SW_WARPS * SW_LCAP * sizeof(double);
+    CU(cudaMemsetAsync(c->flags, 0, sizeof(int), c->stream));       // work counter
+    k_sweep<MODE><<<c->sweep_blocks, SW_WARPS * 32, smem, c->stream>>>(a);
+    LAUNCH_CHECK();
+    return TG_OK;
+}
+
+static int check_flags(tg_ctx *c)
+{
+    int f[4];
+    CU(cudaMemcpyAsync(f, c->flags, sizeof f, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (f[2]) return fail(c, TG_ERANGE, "particle position outside [0, Boxsize] (peano.c:130-132)");
+    if (f[1]) return fail(c, TG_ENOCONV, "hsml iteration did not terminate (fewer than %d gas particles in reach?)", TG_DESNNGB);
+    return TG_OK;
+}
+
+static int density_pass(tg_ctx *c)
+{
+    SweepArgs a = sweep_args(c, 0);
+    int rc = launch_sweep<MODE_DENSITY>(c, a);
+    if (rc) return rc;
+    c->any_cold = false;
+    return TG_OK;
+}
+
+static int carry_state(tg_ctx *c)
+{
+    k_carry<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->pw, c->hsml_out, c->posh);
+    LAUNCH_CHECK();
+    return TG_OK;
+}
+
+static int error_pass(tg_ctx *c, double *err_max, double *err_mean)
+{
+    const int m = c->hi - c->lo;
+    const int nb = cdiv(m, RED_THREADS);
+    k_error<<<nb, RED_THREADS, 0, c->stream>>>(c->lo, c->hi, c->rho, c->rho_model, c->partial);
+    LAUNCH_CHECK();
+    k_final_err<<<1, RED_THREADS, 0, c->stream>>>(nb, c->partial, c->scal + 1);
+    LAUNCH_CHECK();
+    double h[2];
+    CU(cudaMemcpyAsync(h, c->scal + 1, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *err_mean = h[0] / m;     // wvt_relax.c:87 (single rank; multi-rank callers re-reduce)
+    *err_max = h[1];
+    return TG_OK;
+}
+
+static int displacement_pass(tg_ctx *c, double step)
+{
+    SweepArgs a = sweep_args(c, step);
+    if (c->cfg.flags & TG_WVT_SEQUENTIAL) return launch_sweep<MODE_WVT_SEQ>(c, a);
+    return launch_sweep<MODE_WVT>(c, a);
+}
+
+static int move_pass(tg_ctx *c)
+{
+    k_move<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->pw, c->hsml_out, c->delta, c->box.box_d,
+                                                   1.0, c->posh);
+    LAUNCH_CHECK();
+    return TG_OK;
+}
+
+static int finish_stats(tg_ctx *c, bool have_sweep_events)
+{
+    unsigned long long h[4];
+    CU(cudaMemcpyAsync(h, c->counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stats.pair_evals = h[0];
+    c->stats.gathered = h[1];
+    c->stats.searches = h[2];
+    c->stats.hsml_iters = h[3];
+    c->stats.kernels = c->launches;
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    c->stats.step_ms = ms;
+    if (have_sweep_events) {
+        CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
+        c->stats.sweep_ms = ms;
+    }
+    return TG_OK;
+}
+
+// ------------------------------------------------------------------ operators
+
+extern "C" int tg_find_sph_quantities(tg_ctx *c)
+{
+    if (!c) return TG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = reset_counters(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = prepare_index(c))) return rc;
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = density_pass(c))) return rc;
+    CU(cudaEventRecord(c->ev[3], c->stream));
+    if ((rc = carry_state(c))) return rc;
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    if ((rc = check_flags(c))) return rc;
+    return finish_stats(c, true);
+}
+
+extern "C" int tg_wvt_iteration(tg_ctx *c, double step, double *err_max, double *err_mean)
+{
+    if (!c) return TG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = reset_counters(c);
+    if (rc) return rc;
+    double emax = 0, emean = 0;
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = prepare_index(c))) return rc;
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = density_pass(c))) return rc;
+    if ((rc = displacement_pass(c, step))) return rc;
+    CU(cudaEventRecord(c->ev[3], c->stream));
+    if ((rc = error_pass(c, &emax, &emean))) return rc;
+    if ((rc = move_pass(c))) return rc;
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    if ((rc = check_flags(c))) return rc;
+    if (err_max) *err_max = emax;
+    if (err_mean) *err_mean = emean;
+    return finish_stats(c, true);
+}
+
+extern "C" int tg_regularise(tg_ctx *c, int max_iters, tg_log_fn log, void *user, int *iters_done)
+{
+    if (!c) return TG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    // wvt_relax.c:46-59
+    int it = -1, started = 0;
+    double step = 0.0085;
+    if (c->cfg.mtotal < 1e5) step /= 2;
+    double errLast = DBL_MAX, errDiff = DBL_MAX, errDiffLast = DBL_MAX;
+    int rc;
+
+    for (;;) {
+        if (it++ >= TG_NUMITER) break;                       // wvt_relax.c:63
+        if (it >= max_iters) break;                          // test / bench cut-off
+        if ((rc = reset_counters(c))) return rc;
+        CU(cudaEventRecord(c->ev[0], c->stream));
+        if ((rc = prepare_index(c))) return rc;              // wvt_relax.c:67 -> sph.c:15-17
+        CU(cudaEventRecord(c->ev[2], c->stream));
+        if ((rc = density_pass(c))) return rc;               // sph.c:19-72
+        CU(cudaEventRecord(c->ev[3], c->stream));
+        started++;
+
+        double errMax = 0, errMean = 0;
+        if ((rc = error_pass(c, &errMax, &errMean))) return rc;   // wvt_relax.c:73-87
+        if ((rc = check_flags(c))) return rc;
+        errDiff = (errLast - errMean) / errMean;             // wvt_relax.c:89
+        int stop = log ? log(it, errMax, errMean, errDiff, step, user) : 0;
+
+        bool leave = stop != 0;
+        if (errDiff < 0.01 && it > 25) leave = true;         // wvt_relax.c:94
+        if (errDiff < 0 && errDiffLast < 0 && it > 10) leave = true;   // wvt_relax.c:97
+        if (leave) {
+            if ((rc = carry_state(c))) return rc;
+            CU(cudaEventRecord(c->ev[1], c->stream));
+            if ((rc = finish_stats(c, true))) return rc;
+            break;
+        }
+        if (errDiff < 0.01 && it > 1) step *= 0.8;           // wvt_relax.c:100
+        errLast = errMean;
+        errDiffLast = errDiff;
+
+        if ((rc = displacement_pass(c, step))) return rc;    // wvt_relax.c:108-171
+        if ((rc = move_pass(c))) return rc;                  // wvt_relax.c:175-214
+        CU(cudaEventRecord(c->ev[1], c->stream));
+        if ((rc = finish_stats(c, true))) return rc;
+    }
+    if (iters_done) *iters_done = started;
+    return TG_OK;
+}
+
+extern "C" int tg_bfld_from_rotA(tg_ctx *c)
+{
+    if (!c) return TG_EINVAL;
+    if (!c->index_valid) return fail(c, TG_EINVAL, "tg_bfld_from_rotA: no index (call tg_find_sph_quantities first, sph.c:229 reuses the tree)");
+    if (!c->have_apot) return fail(c, TG_EINVAL, "tg_bfld_from_rotA: Apot not set");
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = reset_counters(c);
+    if (rc) return rc;
+    SweepArgs a = sweep_args(c, 0);
+    a.hsml_in = c->hsml_out;    // SphP.Hsml as left by the density call
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = launch_sweep<MODE_ROTA>(c, a))) return rc;
+    CU(cudaEventRecord(c->ev[3], c->stream));
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    return finish_stats(c, true);
+}
+
+extern "C" int tg_get_stats(tg_ctx *c, tg_stats *out)
+{
+    if (!c || !out) return TG_EINVAL;
+    *out = c->stats;
+    return TG_OK;
+}
+
+// ------------------------------------------------------------------ data out
+
+extern "C" int tg_download_soa(tg_ctx *c, float *pos, int32_t *perm, float *hsml, float *rho,
+                               float *varhsml, float *rho_model, float *bfld)
+{
+    if (!c) return TG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    const int n = c->n;
+    CU(cudaStreamSynchronize(c->stream));
+    if (pos || hsml) {
+        std::vector<float4> h(n);
+        CU(cudaMemcpy(h.data(), c->posh, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) {
+            if (pos) { pos[3 * i] = h[i].x; pos[3 * i + 1] = h[i].y; pos[3 * i + 2] = h[i].z; }
+            if (hsml) hsml[i] = h[i].w;
+        }
+    }
+    if (perm) CU(cudaMemcpy(perm, c->id, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (rho) CU(cudaMemcpy(rho, c->rho, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    if (varhsml) CU(cudaMemcpy(varhsml, c->varh, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    if (rho_model) CU(cudaMemcpy(rho_model, c->rho_model, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    if (bfld) CU(cudaMemcpy(bfld, c->bfld, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    return TG_OK;
+}
+
+extern "C" int tg_download(tg_ctx *c, void *P, size_t p_stride, void *SphP, size_t s_stride)
+{
+    if (!c || !P || !SphP || p_stride < 52 || s_stride < 48)
+        return fail(c, TG_EINVAL, "tg_download: records too small for ParticleData / GasParticleData");
+    const int n = c->n;
+    std::vector<float> pos((size_t)3 * n), hsml(n), rho(n), varh(n), rhom(n), bfld((size_t)3 * n);
+    std::vector<int32_t> perm(n);
+    int rc = tg_download_soa(c, pos.data(), perm.data(), hsml.data(), rho.data(), varh.data(),
+                             rhom.data(), bfld.data());
+    if (rc) return rc;
+    std::vector<uint64_t> khi(n), klo(n);
+    if (c->index_valid) {
+        CU(cudaMemcpy(khi.data(), c->key_hi_s, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(klo.data(), c->key_lo_s, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+    }
+    // whole records travel with the particle (peano.c:96-117)
+    std::vector<char> oldP((size_t)n * p_stride), oldS((size_t)n * s_stride);
+    memcpy(oldP.data(), P, oldP.size());
+    memcpy(oldS.data(), SphP, oldS.size());
+    for (int k = 0; k < n; k++) {
+        char *p = (char *)P + (size_t)k * p_stride;
+        char *s = (char *)SphP + (size_t)k * s_stride;
+        memcpy(p, oldP.data() + (size_t)perm[k] * p_stride, p_stride);
+        memcpy(s, oldS.data() + (size_t)perm[k] * s_stride, s_stride);
+        memcpy(p, &pos[3 * (size_t)k], 12);                     // Pos @ +0
+        if (c->index_valid) {
+            memcpy(p + 32, &klo[k], 8);                         // Key @ +32 (little endian u128)
+            memcpy(p + 40, &khi[k], 8);
+            const int parent = k / 32;                          // index group (tree.c's node ids are private)
+            memcpy(p + 48, &parent, 4);                         // Tree_Parent @ +48
+        }
+        float *g = (float *)s;
+        g[1] = rho[k];                                          // Rho @ +4
+        g[2] = hsml[k];                                         // Hsml @ +8
+        g[3] = varh[k];                                         // VarHsmlFac @ +12
+        memcpy(s + 16, &bfld[3 * (size_t)k], 12);               // Bfld @ +16
+        g[11] = rhom[k];                                        // Rho_Model @ +44
+    }
+    return TG_OK;
+}
+
+extern "C" int tg_wvt_scratch(tg_ctx *c, float *hsml_wvt, float *delta)
+{
+    if (!c) return TG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    const int n = c->n;
+    CU(cudaStreamSynchronize(c->stream));
+    if (hsml_wvt) {
+        std::vector<float4> h(n);
+        double vsum = 0;
+        CU(cudaMemcpy(h.data(), c->pw, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&vsum, c->scal, sizeof(double), cudaMemcpyDeviceToHost));
+        const float norm = (float)pow(TG_DESNNGB / vsum / K_FOURPITHIRD, 1.0 / 3.0);   // wvt_relax.c:120
+        for (int i = 0; i < n; i++) hsml_wvt[i] = h[i].w * norm;
+    }
+    if (delta) {
+        std::vector<float> d((size_t)3 * n);
+        CU(cudaMemcpy(d.data(), c->delta, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++)
+            for (int a = 0; a < 3; a++) delta[3 * (size_t)i + a] = d[(size_t)a * n + i];
+    }
+    return TG_OK;
+}
+
+// ------------------------------------------------------------------ test hooks
+
+extern "C" int tg_peano_keys(tg_ctx *c, uint64_t *hi, uint64_t *lo)
+{
+    if (!c || !hi || !lo) return TG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    const int n = c->n;
+    CU(cudaMemsetAsync(c->flags + 2, 0, sizeof(int), c->stream));
+    k_peano_keys<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->posh, c->box.box_d, c->key_hi, c->key_lo,
+                                                     c->idx, c->flags + 2);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(hi, c->key_hi, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(lo, c->key_lo, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    c->index_valid = false;
+    return check_flags(c);
+}
+
+extern "C" int tg_sort(tg_ctx *c, int32_t *perm)
+{
+    if (!c) return TG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = prepare_index(c);
+    if (rc) return rc;
+    // positions and Hsml unchanged: carry them into the new order
+    k_carry<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->pw, c->hsml_in, c->posh);
+    LAUNCH_CHECK();
+    if ((rc = check_flags(c))) return rc;
+    if (perm) CU(cudaMemcpy(perm, c->id, sizeof(int) * c->n, cudaMemcpyDeviceToHost));
+    return TG_OK;
+}
+
+extern "C" int tg_find_ngb(tg_ctx *c, int i, float h, int32_t *list, int *count)
+{
+    if (!c || !list || !count || i < 0 || i >= c->n) return TG_EINVAL;
+    if (!c->index_valid) return fail(c, TG_EINVAL, "tg_find_ngb: no index");
+    CU(cudaSetDevice(c->cfg.device));
+    int *d = nullptr;
+    CU(dmalloc(&d, TG_NGBMAX + 1));
+    k_find_ngb<<<1, 32, 0, c->stream>>>(c->bvh, c->box, c->pw, i, h, d, d + TG_NGBMAX);
+    c->launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(count, d + TG_NGBMAX, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(list, d, sizeof(int) * (*count), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(c, TG_ECUDA, "tg_find_ngb: %s", cudaGetErrorString(e));
+    return TG_OK;
+}
+
+extern "C" int tg_guess_hsml(tg_ctx *c, float *out)
+{
+    if (!c || !out) return TG_EINVAL;
+    if (!c->index_valid) return fail(c, TG_EINVAL, "tg_guess_hsml: no index");
+    CU(cudaSetDevice(c->cfg.device));
+    const int n = c->n, T = 256;
+    k_cpl<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->key_lo_s, c->cpl);
+    LAUNCH_CHECK();
+    k_collapse_events<<<cdiv(n, T), T, 0, c->stream>>>(n, c->cpl, c->ev_start, c->ev_level, c->ev_count);
+    LAUNCH_CHECK();
+    k_guess_hsml<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->key_lo_s, c->cpl, c->ev_start,
+                                                 c->ev_level, c->ev_count, c->box.box_d, c->guess, nullptr);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(out, c->guess, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TG_OK;
+}
+
+extern "C" int tg_get_exchange(tg_ctx *c, tg_exchange *out)
+{
+    if (!c || !out) return TG_EINVAL;
+    out->pos_hsml_dev = c->posh;
+    out->rho_dev = c->rho;
+    out->varhsml_dev = c->varh;
+    out->delta_dev = c->delta;
+    out->err_dev = c->scal + 1;
+    out->lo = c->lo;
+    out->hi = c->hi;
+    return TG_OK;
+}
