@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- WVT relax steps/s and neighbour interactions/s of the SPH/WVT hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of wvt_relax.c:66-214 (Peano sort, index build, WC6 density/hsml solve,
+error pass, model hsml, displacement, move) over the whole synthetic particle set.  The
+default workload is BASELINE.json's metric configuration: the two-cluster merger with
+10 M gas particles (configs[2]); it fits one B200 (about 1.5 GB).  With N > 1 ranks the same
+10 M targets are partitioned by Peano-order slice (strong scaling): every rank sorts and
+indexes all positions redundantly, sweeps its own slice and the moved (x, y, z, Hsml)
+slices are re-assembled with one NCCL all-gather per step.
+
+Printed line (rank 0): value = whole-job steps/s with inputs resident in HBM, device-timed
+(CUDA events on the stream the kernels run on, max over ranks); e2e = the same steps driven
+through the C ABI from pinned host buffers (upload + step + read-back inside the timed
+region); roofline = the sweep kernel's algorithmic bytes / its event-timed duration against
+the measured HBM copy bandwidth; cpu_baseline = the reference's own code (oracle/_ref) on the
+host cores over a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_WORKLOAD = "merger_1e7"
+STEP0 = 0.0085            # wvt_relax.c:51 (Mtotal >= 1e5 in every config)
+CPU_SAMPLE_N = 200_000    # bounded CPU sample: same merger model at reduced N_gas
+L2_BYTES = 126 << 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--n-gas", type=int, default=None, help="override particle count")
+    ap.add_argument("--sequential", action="store_true", help="TG_WVT_SEQUENTIAL")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the sweep kernel from the last committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "sweep_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm
+
+def run_reference(workload_name, n_target, steps, warmup):
+    """The reference's own CPU code (oracle/_ref) on a bounded sample, all host threads."""
+    from toycluster_b200 import workloads
+    from oracle import ref
+    if not ref.available():
+        return None
+    cores = os.cpu_count() or 1
+    n = CPU_SAMPLE_N if n_target > CPU_SAMPLE_N else n_target
+    n = max(n, 256 * cores)                       # wvt_relax.c:127 chunk must stay >= 1
+    w = workloads.make(workload_name, n_gas=n)
+    r = ref.Ref(w.n_gas, w.boxsize, w.mpart_gas, w.mtotal, w.halo_table(), cores)
+    r.load(w.pos)
+    stamps = []
+
+    def cb(it):
+        stamps.append(time.perf_counter())
+        return 0
+
+    total = warmup + steps
+    r.regularise(total, cb)
+    # stamps[k] = start of iteration k; iteration k spans stamps[k]..stamps[k+1]
+    dt = np.diff(np.array(stamps))[warmup:warmup + steps]
+    s_per_step = float(dt.mean())
+    return dict(n_sample=n, cores=r.nthreads, s_per_step_sample=s_per_step,
+                steps_per_s_scaled=(n / n_target) / s_per_step,
+                sample=(f"{workload_name} model at N_gas={n}, {steps} steady-state WVT iterations "
+                        f"after {warmup} warm-up (unmodified reference sources, oracle/_ref), "
+                        f"steps/s scaled by N_gas/{n_target} (cost per particle taken as constant)"))
+
+
+# --------------------------------------------------------------------------- our arm
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from toycluster_b200 import workloads
+    n_gas = args.n_gas or workloads.CONFIGS[args.workload]["n_gas"]
+    config = {"workload": args.workload, "n_gas": n_gas,
+              "parallelism": f"targets partitioned over {world} rank(s), positions replicated",
+              "l2": "inputs larger than L2" if n_gas * 16 > L2_BYTES else "L2 flushed between steps"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        res = run_reference(args.workload, n_gas, args.steps, args.warmup)
+        if res is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libtoyref.so not built"}))
+            return
+        v = res["steps_per_s_scaled"]
+        line = {"metric": "wvt_relax_steps_per_s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64",
+                "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": {"value": v, "unit": "steps/s", "cores": res["cores"],
+                                 "kind": "reference", "sample": res["sample"]},
+                "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import toycluster_b200 as tc
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()            # the library launches on this stream, so the
+    torch.cuda.set_stream(stream)           # events below see exactly its kernels
+
+    w = workloads.make(args.workload, n_gas=n_gas)          # same seed on every rank
+    flags = tc.WVT_SEQUENTIAL if args.sequential else 0
+    g = tc.HotPath.from_workload(w, device=local_rank, flags=flags, rank=rank, nranks=world,
+                                 stream=stream.cuda_stream)
+    n = w.n_gas
+    ex = g.exchange()
+    chunk, npad = ex.chunk, ex.chunk * world
+
+    class _Dev:     # wrap library-owned device memory as a torch tensor (zero copy)
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1",
+                                             "data": (ptr, False), "version": 2}
+
+    posh_full = torch.as_tensor(_Dev(ex.pos_hsml_dev, npad * 16), device="cuda").view(torch.float32)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if n * 16 <= L2_BYTES else None
+
+    def exchange():
+        if world > 1:
+            mine = posh_full[rank * chunk * 4:(rank + 1) * chunk * 4]
+            dist.all_gather_into_tensor(posh_full, mine)
+
+    def one_step(step):
+        if flush is not None:
+            flush.zero_()
+        g.wvt_iteration(step)
+        exchange()
+        return g.stats()
+
+    # pinned host state for the e2e leg
+    pos_host = torch.from_numpy(w.pos).pin_memory()
+    hsml_host = torch.zeros(n, dtype=torch.float32).pin_memory()
+    pos_np, hsml_np = pos_host.numpy(), hsml_host.numpy()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- resident-in-HBM timing -------------------------------------------------------
+    g.upload(pos_np)
+    step = STEP0
+    for _ in range(args.warmup):
+        one_step(step)
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc = dict(pair_evals=0, gathered=0, kernels=0, sweep_ms=0.0, step_ms=0.0)
+    t_wall = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        s = one_step(step)
+        for k in acc:
+            acc[k] += s[k]
+    e1.record(stream)
+    sync_all()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+
+    red = torch.tensor([ms_total, t_wall * 1e3, acc["sweep_ms"]], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(acc["pair_evals"]), float(acc["gathered"])], dtype=torch.float64,
+                       device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total, wall_ms, sweep_ms_max = red.tolist()
+    pair_evals, gathered = tot.tolist()
+
+    # ---- end to end through the C ABI with host buffers --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        out = g.download()
+        pos_np[:] = out["pos"]
+        hsml_np[:] = out["hsml"]
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            g.upload(pos_np, hsml_np)                        # H2D from pinned memory
+            g.wvt_iteration(step)
+            exchange()
+            if world > 1:
+                torch.cuda.synchronize()
+            g.lib.tg_download_soa(g._ctx, pos_np.ctypes.data, None, hsml_np.ctypes.data,
+                                  None, None, None, None)   # D2H of the step's result
+        sync_all()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": args.steps / dt.item(), "unit": "steps/s",
+               "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
+               "ms_per_step": dt.item() * 1e3 / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = ms_total / args.steps
+    value = 1e3 / ms_per_step
+    peak, peak_kind = measured_peak()
+    # algorithmic bytes of the sweep launch: 40 B per target (own x,y,z,h read,
+    # Hsml/Rho/VarHsmlFac + displacement written) + 16 B per distinct gathered neighbour
+    sweep_bytes = (40.0 * n + 16.0 * gathered / args.steps) / world
+    sweep_ms = sweep_ms_max / args.steps
+    achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "k_sweep<density+wvt>", "achieved": achieved, "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic["bytes_per_launch"] if traffic else None,
+                "sweep_ms": sweep_ms, "sweep_share_of_step": sweep_ms / ms_per_step,
+                "step_bytes_model": 300.0 * n + 16.0 * gathered / args.steps,
+                "step_frac": (300.0 * n + 16.0 * gathered / args.steps) / world
+                             / (ms_per_step * 1e-3) / 1e9 / peak}
+
+    line = {"metric": "wvt_relax_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 predicate / f64 sums (reference's mixed precision)",
+            "data": "synthetic", "config": config,
+            "interactions_per_s": pair_evals / args.steps * value,
+            "pair_evals_per_particle": pair_evals / args.steps / n,
+            "gathered_per_particle": gathered / args.steps / n,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "gpu_launches": int(acc["kernels"]), "clocks": clocks, "roofline": roofline}
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        res = run_reference(args.workload, n, 2, 1)
+        if res:
+            line["cpu_baseline"] = {"value": res["steps_per_s_scaled"], "unit": "steps/s",
+                                    "cores": res["cores"], "kind": "reference",
+                                    "sample": res["sample"],
+                                    "s_per_step_sample": res["s_per_step_sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -60,6 +60,7 @@ typedef struct {
     double mtotal;       /* Param.Mtotal (wvt_relax.c:53) */
     unsigned flags;
     int rank, nranks;    /* target-particle partition; 0,1 for one GPU */
+    void *stream;        /* cudaStream_t to run on (e.g. the caller's NCCL stream); NULL = own */
 } tg_config;
 
 typedef struct tg_ctx tg_ctx;
@@ -140,7 +141,9 @@ typedef struct {
     void *varhsml_dev;    /* float[n]  */
     void *delta_dev;      /* float[3][n] */
     void *err_dev;        /* double[2]: sum err, max err of the local slice */
-    int lo, hi;
+    int lo, hi;           /* this rank's targets: [rank*chunk, min(n, (rank+1)*chunk)) */
+    int chunk;            /* pos_hsml/rho/varhsml are allocated nranks*chunk elements long, so
+                             an in-place all-gather of `chunk` elements per rank fills them */
 } tg_exchange;
 int tg_get_exchange(tg_ctx *ctx, tg_exchange *out);
 

@@ -43,7 +43,7 @@ class _Halo(C.Structure):
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int), ("n_gas", C.c_int), ("boxsize", C.c_double),
                 ("mpart_gas", C.c_double), ("mtotal", C.c_double), ("flags", C.c_uint),
-                ("rank", C.c_int), ("nranks", C.c_int)]
+                ("rank", C.c_int), ("nranks", C.c_int), ("stream", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -58,7 +58,7 @@ class Stats(C.Structure):
 class _Exchange(C.Structure):
     _fields_ = [("pos_hsml_dev", C.c_void_p), ("rho_dev", C.c_void_p),
                 ("varhsml_dev", C.c_void_p), ("delta_dev", C.c_void_p),
-                ("err_dev", C.c_void_p), ("lo", C.c_int), ("hi", C.c_int)]
+                ("err_dev", C.c_void_p), ("lo", C.c_int), ("hi", C.c_int), ("chunk", C.c_int)]
 
 
 _LOG_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -129,12 +129,12 @@ class HotPath:
     """One device context == the global state the reference's path works on."""
 
     def __init__(self, n_gas, boxsize, mpart_gas, mtotal, halo_table, device=0, flags=0,
-                 rank=0, nranks=1):
+                 rank=0, nranks=1, stream=None):
         self.lib = load()
         self.n = int(n_gas)
         self._ctx = C.c_void_p()
         cfg = _Config(int(device), self.n, float(boxsize), float(mpart_gas), float(mtotal),
-                      int(flags), int(rank), int(nranks))
+                      int(flags), int(rank), int(nranks), C.c_void_p(stream or None))
         rc = self.lib.tg_create(C.byref(self._ctx), C.byref(cfg))
         if rc != 0:
             msg = self.lib.tg_last_error(None).decode()

@@ -147,12 +147,12 @@ k_final_err(int count, const double *__restrict__ partial, double *__restrict__ 
 // wvt_relax.c:193-213: Pos += (float)(delta * boxsize), wrap into [0, Boxsize]; the result
 // (with the freshly solved Hsml) becomes the next iteration's unsorted input.
 // `scale` rescales a displacement computed with a stale step (fused sweep); 1 otherwise.
-__global__ void k_move(int n, const float4 *__restrict__ pw, const float *__restrict__ hsml,
-                       const float *__restrict__ delta, double box, double scale,
-                       float4 *__restrict__ posh_out)
+__global__ void k_move(int lo, int hi, int n, const float4 *__restrict__ pw,
+                       const float *__restrict__ hsml, const float *__restrict__ delta, double box,
+                       double scale, float4 *__restrict__ posh_out)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    const int k = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= hi) return;
     const float4 p = pw[k];
     float c[3] = {p.x, p.y, p.z};
 #pragma unroll
@@ -168,11 +168,33 @@ __global__ void k_move(int n, const float4 *__restrict__ pw, const float *__rest
 }
 
 // No displacement: carry (x, y, z, Hsml) of the sorted order into the next input buffer.
-__global__ void k_carry(int n, const float4 *__restrict__ pw, const float *__restrict__ hsml,
-                        float4 *__restrict__ posh_out)
+__global__ void k_carry(int lo, int hi, const float4 *__restrict__ pw,
+                        const float *__restrict__ hsml, float4 *__restrict__ posh_out)
+{
+    const int k = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= hi) return;
+    const float4 p = pw[k];
+    posh_out[k] = make_float4(p.x, p.y, p.z, hsml[k]);
+}
+
+// Host SoA staging <-> packed state. cold_flag is raised when any Hsml is 0 (sph.c:25).
+__global__ void k_pack_state(int n, const float *__restrict__ pos, const float *__restrict__ hsml,
+                             float4 *__restrict__ posh, int *__restrict__ id, int *__restrict__ cold_flag)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const float4 p = pw[k];
-    posh_out[k] = make_float4(p.x, p.y, p.z, hsml[k]);
+    const float h = hsml ? hsml[k] : 0.f;
+    posh[k] = make_float4(pos[3 * (size_t)k], pos[3 * (size_t)k + 1], pos[3 * (size_t)k + 2], h);
+    id[k] = k;
+    if (h == 0.f) *cold_flag = 1;
+}
+
+__global__ void k_unpack_state(int n, const float4 *__restrict__ posh, float *__restrict__ pos,
+                               float *__restrict__ hsml)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 p = posh[k];
+    pos[3 * (size_t)k] = p.x; pos[3 * (size_t)k + 1] = p.y; pos[3 * (size_t)k + 2] = p.z;
+    hsml[k] = p.w;
 }

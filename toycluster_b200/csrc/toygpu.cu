@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -33,7 +34,8 @@ struct tg_ctx {
     tg_config cfg{};
     std::string err;
     cudaStream_t stream = nullptr;
-    int n = 0, lo = 0, hi = 0;
+    bool own_stream = false;
+    int n = 0, lo = 0, hi = 0, chunk = 0;
     Box box{};
     double bias_const = 0;
 
@@ -41,6 +43,7 @@ struct tg_ctx {
     float4 *posh = nullptr;
     int *id = nullptr;
     float *apot = nullptr;          // [n][3] or null
+    float *stage = nullptr;         // [4n] host<->device staging (pos[n][3], hsml[n])
     bool have_apot = false;
     bool any_cold = true;
     bool index_valid = false;
@@ -79,7 +82,7 @@ struct tg_ctx {
     double *partial = nullptr;      // block partials
     int npartial = 0;
     double *scal = nullptr;         // [0] vsum, [1] err sum, [2] err max
-    int *flags = nullptr;           // [0] next, [1] status, [2] range_err, [3] n_tied
+    int *flags = nullptr;           // [0] next, [1] status, [2] range_err, [3] n_tied, [4] cold
     unsigned long long *counters = nullptr;   // 4
     double *gscratch = nullptr;
     int sweep_blocks = 0;
@@ -135,14 +138,14 @@ extern "C" int tg_destroy(tg_ctx *c)
 {
     if (!c) return TG_OK;
     cudaSetDevice(c->cfg.device);
-    void *ptrs[] = {c->posh, c->id, c->apot, c->key_hi, c->key_lo, c->key_tmp, c->idx, c->idx_tmp,
+    void *ptrs[] = {c->posh, c->id, c->apot, c->stage, c->key_hi, c->key_lo, c->key_tmp, c->idx, c->idx_tmp,
                     c->hist, c->pw, c->hsml_in, c->rho_model, c->id_s, c->key_lo_s, c->apot_s,
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->cpl,
                     c->ev_level, c->ev_count, c->ev_start, c->guess, c->halos, c->partial, c->scal,
                     c->flags, c->counters, c->gscratch};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return TG_OK;
 }
@@ -171,8 +174,12 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     c->cfg = *cfg;
     c->cfg.nranks = nranks;
     const int n = c->n = cfg->n_gas;
-    c->lo = (int)((long long)n * cfg->rank / nranks);
-    c->hi = (int)((long long)n * (cfg->rank + 1) / nranks);
+    // equal-sized slices (the last may be short) so one all-gather of `chunk` elements per
+    // rank reassembles an array; exchanged arrays are padded to nranks*chunk
+    c->chunk = (n + nranks - 1) / nranks;
+    c->lo = std::min(n, cfg->rank * c->chunk);
+    c->hi = std::min(n, c->lo + c->chunk);
+    const size_t npad = (size_t)c->chunk * nranks;
 
     c->box.box_d = cfg->boxsize;
     c->box.boxhalf_d = 0.5 * cfg->boxsize;            // sph.c:83
@@ -193,11 +200,13 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     } while (0)
 
     CUC(cudaSetDevice(cfg->device));
-    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
+    else { CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     for (auto &ev : c->ev) CUC(cudaEventCreate(&ev));
 
-    CUC(dmalloc(&c->posh, n));
+    CUC(dmalloc(&c->posh, npad));
     CUC(dmalloc(&c->id, n));
+    CUC(dmalloc(&c->stage, (size_t)4 * n));
     CUC(dmalloc(&c->key_hi, n));
     CUC(dmalloc(&c->key_lo, n));
     CUC(dmalloc(&c->key_tmp, n));
@@ -211,8 +220,8 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     CUC(dmalloc(&c->id_s, n));
     CUC(dmalloc(&c->key_lo_s, n));
     CUC(dmalloc(&c->hsml_out, n));
-    CUC(dmalloc(&c->rho, n));
-    CUC(dmalloc(&c->varh, n));
+    CUC(dmalloc(&c->rho, npad));
+    CUC(dmalloc(&c->varh, npad));
     CUC(dmalloc(&c->delta, (size_t)3 * n));
     CUC(dmalloc(&c->bfld, (size_t)3 * n));
     CUC(cudaMemsetAsync(c->rho, 0, sizeof(float) * n, c->stream));
@@ -251,9 +260,9 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     c->npartial = cdiv(n, RED_THREADS);
     CUC(dmalloc(&c->partial, (size_t)2 * c->npartial));
     CUC(dmalloc(&c->scal, 4));
-    CUC(dmalloc(&c->flags, 4));
+    CUC(dmalloc(&c->flags, 8));
     CUC(dmalloc(&c->counters, 4));
-    CUC(cudaMemsetAsync(c->flags, 0, 4 * sizeof(int), c->stream));
+    CUC(cudaMemsetAsync(c->flags, 0, 8 * sizeof(int), c->stream));
     CUC(cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned long long), c->stream));
 
     // sweep grid: every SM full of resident blocks (persistent, work-stealing)
@@ -301,17 +310,23 @@ extern "C" int tg_set_halos(tg_ctx *c, int n, const tg_halo *h)
 
 // ------------------------------------------------------------------ data in
 
-static int upload_common(tg_ctx *c, const std::vector<float4> &posh)
+// Host SoA -> device staging (plain cudaMemcpyAsync, DMA when the host buffer is pinned),
+// then one kernel packs (x, y, z, Hsml) and writes the identity ids.
+static int upload_common(tg_ctx *c, const float *pos, const float *hsml)
 {
     const int n = c->n;
     CU(cudaSetDevice(c->cfg.device));
-    std::vector<int> ids(n);
-    bool cold = false;
-    for (int i = 0; i < n; i++) { ids[i] = i; cold |= posh[i].w == 0; }
-    CU(cudaMemcpyAsync(c->posh, posh.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->id, ids.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->stage, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    if (hsml)
+        CU(cudaMemcpyAsync(c->stage + 3 * (size_t)n, hsml, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->flags + 4, 0, sizeof(int), c->stream));
+    k_pack_state<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->stage, hsml ? c->stage + 3 * (size_t)n : nullptr,
+                                                     c->posh, c->id, c->flags + 4);
+    LAUNCH_CHECK();
+    int cold = 0;
+    CU(cudaMemcpyAsync(&cold, c->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->any_cold = cold;
+    c->any_cold = cold != 0;
     c->index_valid = false;
     c->have_apot = false;
     return TG_OK;
@@ -320,26 +335,24 @@ static int upload_common(tg_ctx *c, const std::vector<float4> &posh)
 extern "C" int tg_upload_soa(tg_ctx *c, const float *pos, const float *hsml)
 {
     if (!c || !pos) return fail(c, TG_EINVAL, "tg_upload_soa: null argument");
-    std::vector<float4> posh(c->n);
-    for (int i = 0; i < c->n; i++)
-        posh[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], hsml ? hsml[i] : 0.f);
-    return upload_common(c, posh);
+    return upload_common(c, pos, hsml);
 }
 
 extern "C" int tg_upload(tg_ctx *c, const void *P, size_t p_stride, const void *SphP, size_t s_stride)
 {
     if (!c || !P || !SphP || p_stride < 12 || s_stride < 12)
         return fail(c, TG_EINVAL, "tg_upload: bad arguments");
-    std::vector<float4> posh(c->n);
+    std::vector<float> pos((size_t)3 * c->n), hsml(c->n);
     std::vector<float> apot((size_t)3 * c->n);
     const bool with_apot = s_stride >= 40;
     for (int i = 0; i < c->n; i++) {
-        const float *pos = (const float *)((const char *)P + i * p_stride);            // Pos @ +0
+        const float *pp = (const float *)((const char *)P + i * p_stride);             // Pos @ +0
         const float *sph = (const float *)((const char *)SphP + i * s_stride);
-        posh[i] = make_float4(pos[0], pos[1], pos[2], sph[2]);                          // Hsml @ +8
+        pos[3 * (size_t)i] = pp[0]; pos[3 * (size_t)i + 1] = pp[1]; pos[3 * (size_t)i + 2] = pp[2];
+        hsml[i] = sph[2];                                                               // Hsml @ +8
         if (with_apot) for (int k = 0; k < 3; k++) apot[3 * (size_t)i + k] = sph[7 + k];   // Apot @ +28
     }
-    int rc = upload_common(c, posh);
+    int rc = upload_common(c, pos.data(), hsml.data());
     if (rc == TG_OK && with_apot) rc = tg_set_apot(c, apot.data());
     return rc;
 }
@@ -506,7 +519,8 @@ static int density_pass(tg_ctx *c)
 
 static int carry_state(tg_ctx *c)
 {
-    k_carry<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->pw, c->hsml_out, c->posh);
+    if (c->hi > c->lo)
+        k_carry<<<cdiv(c->hi - c->lo, 256), 256, 0, c->stream>>>(c->lo, c->hi, c->pw, c->hsml_out, c->posh);
     LAUNCH_CHECK();
     return TG_OK;
 }
@@ -522,7 +536,7 @@ static int error_pass(tg_ctx *c, double *err_max, double *err_mean)
     double h[2];
     CU(cudaMemcpyAsync(h, c->scal + 1, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    *err_mean = h[0] / m;     // wvt_relax.c:87 (single rank; multi-rank callers re-reduce)
+    *err_mean = m > 0 ? h[0] / m : 0;   // wvt_relax.c:87 (local slice; multi-rank callers re-reduce)
     *err_max = h[1];
     return TG_OK;
 }
@@ -536,8 +550,9 @@ static int displacement_pass(tg_ctx *c, double step)
 
 static int move_pass(tg_ctx *c)
 {
-    k_move<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->pw, c->hsml_out, c->delta, c->box.box_d,
-                                                   1.0, c->posh);
+    if (c->hi > c->lo)
+        k_move<<<cdiv(c->hi - c->lo, 256), 256, 0, c->stream>>>(c->lo, c->hi, c->n, c->pw, c->hsml_out, c->delta,
+                                                               c->box.box_d, 1.0, c->posh);
     LAUNCH_CHECK();
     return TG_OK;
 }
@@ -591,8 +606,14 @@ extern "C" int tg_wvt_iteration(tg_ctx *c, double step, double *err_max, double 
     CU(cudaEventRecord(c->ev[0], c->stream));
     if ((rc = prepare_index(c))) return rc;
     CU(cudaEventRecord(c->ev[2], c->stream));
-    if ((rc = density_pass(c))) return rc;
-    if ((rc = displacement_pass(c, step))) return rc;
+    if (c->cfg.flags & TG_WVT_SEQUENTIAL) {
+        if ((rc = density_pass(c))) return rc;
+        if ((rc = displacement_pass(c, step))) return rc;
+    } else {   // one sweep: density solve and displacement share the walk over HBM
+        SweepArgs a = sweep_args(c, step);
+        if ((rc = launch_sweep<MODE_DENSITY | MODE_WVT>(c, a))) return rc;
+        c->any_cold = false;
+    }
     CU(cudaEventRecord(c->ev[3], c->stream));
     if ((rc = error_pass(c, &emax, &emean))) return rc;
     if ((rc = move_pass(c))) return rc;
@@ -686,20 +707,19 @@ extern "C" int tg_download_soa(tg_ctx *c, float *pos, int32_t *perm, float *hsml
     if (!c) return TG_EINVAL;
     CU(cudaSetDevice(c->cfg.device));
     const int n = c->n;
-    CU(cudaStreamSynchronize(c->stream));
+    cudaStream_t st = c->stream;
     if (pos || hsml) {
-        std::vector<float4> h(n);
-        CU(cudaMemcpy(h.data(), c->posh, sizeof(float4) * n, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < n; i++) {
-            if (pos) { pos[3 * i] = h[i].x; pos[3 * i + 1] = h[i].y; pos[3 * i + 2] = h[i].z; }
-            if (hsml) hsml[i] = h[i].w;
-        }
+        k_unpack_state<<<cdiv(n, 256), 256, 0, st>>>(n, c->posh, c->stage, c->stage + 3 * (size_t)n);
+        LAUNCH_CHECK();
+        if (pos) CU(cudaMemcpyAsync(pos, c->stage, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+        if (hsml) CU(cudaMemcpyAsync(hsml, c->stage + 3 * (size_t)n, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     }
-    if (perm) CU(cudaMemcpy(perm, c->id, sizeof(int) * n, cudaMemcpyDeviceToHost));
-    if (rho) CU(cudaMemcpy(rho, c->rho, sizeof(float) * n, cudaMemcpyDeviceToHost));
-    if (varhsml) CU(cudaMemcpy(varhsml, c->varh, sizeof(float) * n, cudaMemcpyDeviceToHost));
-    if (rho_model) CU(cudaMemcpy(rho_model, c->rho_model, sizeof(float) * n, cudaMemcpyDeviceToHost));
-    if (bfld) CU(cudaMemcpy(bfld, c->bfld, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost));
+    if (perm) CU(cudaMemcpyAsync(perm, c->id, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    if (rho) CU(cudaMemcpyAsync(rho, c->rho, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    if (varhsml) CU(cudaMemcpyAsync(varhsml, c->varh, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    if (rho_model) CU(cudaMemcpyAsync(rho_model, c->rho_model, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    if (bfld) CU(cudaMemcpyAsync(bfld, c->bfld, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return TG_OK;
 }
 
@@ -791,7 +811,7 @@ extern "C" int tg_sort(tg_ctx *c, int32_t *perm)
     int rc = prepare_index(c);
     if (rc) return rc;
     // positions and Hsml unchanged: carry them into the new order
-    k_carry<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->pw, c->hsml_in, c->posh);
+    k_carry<<<cdiv(c->n, 256), 256, 0, c->stream>>>(0, c->n, c->pw, c->hsml_in, c->posh);
     LAUNCH_CHECK();
     if ((rc = check_flags(c))) return rc;
     if (perm) CU(cudaMemcpy(perm, c->id, sizeof(int) * c->n, cudaMemcpyDeviceToHost));
@@ -843,5 +863,6 @@ extern "C" int tg_get_exchange(tg_ctx *c, tg_exchange *out)
     out->err_dev = c->scal + 1;
     out->lo = c->lo;
     out->hi = c->hi;
+    out->chunk = c->chunk;
     return TG_OK;
 }
