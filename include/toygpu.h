@@ -79,6 +79,8 @@ typedef struct {
     unsigned long long kernels;      /* kernel launches */
     double sweep_ms;                 /* device time of the neighbour sweep kernel(s) */
     double step_ms;                  /* device time of the whole step */
+    unsigned long long handed_back;  /* targets the tile sweep returned to the generic sweep
+                                        (last sweep launch of the step) */
 } tg_stats;
 
 /* ---- life cycle -------------------------------------------------------------------- */

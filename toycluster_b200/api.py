@@ -49,7 +49,8 @@ class _Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("pair_evals", C.c_ulonglong), ("gathered", C.c_ulonglong),
                 ("searches", C.c_ulonglong), ("hsml_iters", C.c_ulonglong),
-                ("kernels", C.c_ulonglong), ("sweep_ms", C.c_double), ("step_ms", C.c_double)]
+                ("kernels", C.c_ulonglong), ("sweep_ms", C.c_double), ("step_ms", C.c_double),
+                ("handed_back", C.c_ulonglong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

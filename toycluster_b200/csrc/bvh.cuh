@@ -92,28 +92,24 @@ static __device__ __forceinline__ float box_dist2(float x, float y, float z, flo
     return dx * dx + dy * dy + dz * dz;
 }
 
-// Warp-cooperative ordered walk: calls visit(group) for every level-0 box within `radius`
-// of (x,y,z), in ascending group order (hence ascending particle index, like the depth-first
-// walk of tree.c:35-108).  visit returns false to stop early.  All 32 lanes must call this
-// with identical arguments.  Per-level state (pending-children mask, parent index) lives in
-// the registers of lane == level, so the walk uses no local or shared memory.
-template <class Visit>
-static __device__ __forceinline__ void bvh_walk(const Bvh &t, const Box &bx, float x, float y,
-                                                float z, float radius, Visit &&visit)
+// Warp-cooperative ordered walk: calls visit(group) for every level-0 box accepted by
+// test(o) (o = index into the box arrays; the test must be monotone, i.e. accept every
+// ancestor of an accepted box), in ascending group order -- hence ascending particle index,
+// like the depth-first walk of tree.c:35-108.  visit returns false to stop early.  All 32
+// lanes must call this with identical arguments.  Per-level state (pending-children mask,
+// parent index) lives in the registers of lane == level, so the walk uses no local or shared
+// memory.
+template <class Test, class Visit>
+static __device__ __forceinline__ void bvh_walk_pred(const Bvh &t, Test &&test, Visit &&visit)
 {
     const int lane = lane_id();
-    const float r2 = radius * radius * 1.00001f;
     unsigned my_mask = 0;
     int my_parent = 0;
 
     auto test_children = [&](int level, int parent) -> unsigned {
         const int k = parent * 32 + lane;
         bool hit = false;
-        if (k < t.lvl_n[level]) {
-            const int o = t.lvl_off[level] + k;
-            hit = box_dist2(x, y, z, t.cx[o], t.cy[o], t.cz[o], t.hx[o], t.hy[o], t.hz[o],
-                            bx.box_f, bx.boxhalf_f) <= r2;
-        }
+        if (k < t.lvl_n[level]) hit = test(t.lvl_off[level] + k);
         return __ballot_sync(FULL_MASK, hit);
     };
 
@@ -141,4 +137,16 @@ static __device__ __forceinline__ void bvh_walk(const Bvh &t, const Box &bx, flo
             if (lane == level) { my_mask = cm; my_parent = child; }
         }
     }
+}
+
+// Boxes within `radius` of the point (x,y,z).
+template <class Visit>
+static __device__ __forceinline__ void bvh_walk(const Bvh &t, const Box &bx, float x, float y,
+                                                float z, float radius, Visit &&visit)
+{
+    const float r2 = radius * radius * 1.00001f;
+    bvh_walk_pred(t, [&](int o) -> bool {
+        return box_dist2(x, y, z, t.cx[o], t.cy[o], t.cz[o], t.hx[o], t.hy[o], t.hz[o],
+                         bx.box_f, bx.boxhalf_f) <= r2;
+    }, visit);
 }

@@ -1,0 +1,352 @@
+// tile.cuh -- sweep v2: the warm-start fast path of the neighbour sweep.
+//
+// ncu on sweep v1 (profiles/r01_v1_*) showed an issue-bound kernel spending ~22 % of its
+// instructions walking the box hierarchy once per target and ~25 % on a candidate scan that
+// is only 8 % efficient.  Consecutive Peano-ordered targets have almost the same
+// neighbourhood, so v2 shares that work across a TILE of 32 consecutive targets (one leaf
+// box of the index):
+//
+//   k_tile_walk   one warp per tile: R = max over the tile of the largest radius any of its
+//                 targets can need without a third search (1.23*Hsml, sph.c:51, and the WVT
+//                 radius, wvt_relax.c:135); ordered walk with a box-to-box distance test
+//                 -> ascending list of candidate boxes in global memory.
+//   k_sweep_tile  one 8-warp block per tile:
+//     phase 1  one LANE per TARGET, all lanes read the same candidate (one broadcast 16-byte
+//              load per candidate, served by L1/L2): the exact float predicate of
+//              tree.c:67-88 for radius R_i -> one bit per (target, candidate) in a
+//              shared-memory bit matrix.  No divergence, no ballots, no per-target walk.
+//     phase 2  one WARP per target: expand the target's bit row into a compact candidate
+//              list, classify each hit against Hsml, 1.23*Hsml and the WVT radius, build the
+//              FP64 separation list with full lanes, run Find_hsml (sph.c:80-214) and the
+//              displacement sum (wvt_relax.c:137-170) -- all with the same arithmetic as v1.
+//   Anything outside the fast path's envelope (cold start, list overflow, a third search,
+//   Find_hsml not converging on the frozen list) is pushed to a work list and redone from
+//   scratch by the generic v1 kernel, so results do not depend on which path ran.
+#pragma once
+#include "common.cuh"
+#include "bvh.cuh"
+#include "sph.cuh"
+
+#define TL_WARPS 8
+#define TL_GROUPS 288                    // candidate boxes per tile (median ~150 at 1 M)
+#define TL_UCAP 896                      // hits within R_i kept per target
+#define TL_LCAP 640                      // density list entries per target
+#define TL_MSTRIDE 33                    // bit-matrix row stride (words), odd => no bank conflicts
+
+// shared memory layout (bytes): bit matrix, box list, per-warp lists
+#define TL_OFF_MASK 0
+#define TL_OFF_GRP (TL_OFF_MASK + TL_GROUPS * TL_MSTRIDE * 4)
+#define TL_OFF_RL (TL_OFF_GRP + TL_GROUPS * 4)
+#define TL_OFF_UL (TL_OFF_RL + TL_WARPS * TL_LCAP * 8)
+#define TL_OFF_MISC (TL_OFF_UL + TL_WARPS * TL_UCAP * 2)
+#define TL_SMEM (TL_OFF_MISC + 64)
+
+// Periodic gap^2 between two boxes (centre/half-width form).
+static __device__ __forceinline__ float box_box_dist2(float ax, float ay, float az, float ahx,
+                                                      float ahy, float ahz, float bx, float by,
+                                                      float bz, float bhx, float bhy, float bhz,
+                                                      float box, float boxhalf)
+{
+    float dx = fabsf(ax - bx), dy = fabsf(ay - by), dz = fabsf(az - bz);
+    if (dx > boxhalf) dx = box - dx;
+    if (dy > boxhalf) dy = box - dy;
+    if (dz > boxhalf) dz = box - dz;
+    dx = fmaxf(dx - (ahx + bhx), 0.f);
+    dy = fmaxf(dy - (ahy + bhy), 0.f);
+    dz = fmaxf(dz - (ahz + bhz), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// Largest search radius target i can need on the fast path.
+static __device__ __forceinline__ float tile_radius(float hA, float hw_raw, float norm, double box)
+{
+    const float hB = (float)((double)hA * 1.23);                   // sph.c:51
+    const float hsw = (float)((double)__fmul_rn(hw_raw, norm) * box);   // wvt_relax.c:124,135
+    return fmaxf(hB, hsw);
+}
+
+// tile_ng[tile] = number of candidate boxes (bit 30 set: no target of the tile can see a
+// periodic image, so phase 1 may skip the wrap), or -1 when the tile must take the generic
+// path.  One warp per tile.
+__global__ void k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw,
+                            const float *__restrict__ hsml_in, const double *__restrict__ vsum,
+                            int tile_lo, int tile_hi, int *__restrict__ tile_ng,
+                            int *__restrict__ tile_groups)
+{
+    const int tile = tile_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (tile >= tile_hi) return;
+    const int lane = lane_id();
+    const int i = tile * 32 + lane;
+    const float norm = (float)pow(TG_DESNNGB / *vsum / K_FOURPITHIRD, 1.0 / 3.0);
+
+    float R = 0;
+    bool cold = false;
+    if (i < t.n) {
+        const float hA = hsml_in[i];
+        cold = hA == 0;
+        R = tile_radius(hA, pw[i].w, norm, bx.box_d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) R = fmaxf(R, __shfl_xor_sync(FULL_MASK, R, o));
+    if (__any_sync(FULL_MASK, cold) || !(R < bx.boxhalf_f)) {
+        if (lane == 0) tile_ng[tile] = -1;
+        return;
+    }
+    const float ax = t.cx[tile], ay = t.cy[tile], az = t.cz[tile];
+    const float ahx = t.hx[tile], ahy = t.hy[tile], ahz = t.hz[tile];
+    const float R2 = R * R * 1.00001f;
+    int ng = 0;
+    int *out = tile_groups + (size_t)tile * TL_GROUPS;
+    bvh_walk_pred(t, [&](int o) -> bool {
+        return box_box_dist2(ax, ay, az, ahx, ahy, ahz, t.cx[o], t.cy[o], t.cz[o], t.hx[o], t.hy[o],
+                             t.hz[o], bx.box_f, bx.boxhalf_f) <= R2;
+    }, [&](int g) -> bool {
+        if (ng < TL_GROUPS && lane == 0) out[ng] = g;
+        ng++;
+        return ng < 8192;        // keep counting past the cap: the count feeds diagnostics
+    });
+    if (lane == 0) {
+        if (ng > TL_GROUPS) tile_ng[tile] = -ng;
+        else {
+            const float m = R * 1.0001f;   // margin: a wrapped pair must stay a miss after rounding
+            const bool interior = ax - ahx - m >= 0 && ax + ahx + m <= bx.box_f &&
+                                  ay - ahy - m >= 0 && ay + ahy + m <= bx.box_f &&
+                                  az - ahz - m >= 0 && az + ahz + m <= bx.box_f;
+            tile_ng[tile] = ng | (interior ? (1 << 30) : 0);
+        }
+    }
+}
+
+struct TileList {     // density list: r as double; the sign bit marks "outside the Hsml list"
+    double *sm;
+    __device__ __forceinline__ double get(int k) const { return fabs(sm[k]); }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TL_WARPS * 32, 2) k_sweep_tile(const SweepArgs a, int tile_lo,
+                                                                   int tile_hi)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned *s_mask = (unsigned *)(smem + TL_OFF_MASK);
+    int *s_grp = (int *)(smem + TL_OFF_GRP);
+    int *s_misc = (int *)(smem + TL_OFF_MISC);       // [0] tile, [1] next target
+
+    const int lane = lane_id();
+    const int w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1;
+    double *rl = (double *)(smem + TL_OFF_RL) + w * TL_LCAP;
+    unsigned short *ul = (unsigned short *)(smem + TL_OFF_UL) + w * TL_UCAP;
+    TileList L{rl};
+
+    const float norm = (float)pow(TG_DESNNGB / *a.vsum / K_FOURPITHIRD, 1.0 / 3.0);   // wvt_relax.c:120
+    const float box = a.bx.box_f, boxhalf = a.bx.boxhalf_f;
+    const int n = a.t.n;
+
+    unsigned long long c_evals = 0, c_gath = 0, c_pairs = 0;
+    unsigned c_search = 0, c_iters = 0;
+
+    auto hand_back = [&](int i) {     // redo target i on the generic path
+        if (lane == 0) a.worklist[atomicAdd(a.nwork, 1)] = i;
+    };
+
+    for (;;) {
+        __syncthreads();              // previous tile fully consumed
+        if (threadIdx.x == 0) { s_misc[0] = atomicAdd(a.next, 1); s_misc[1] = 0; }
+        __syncthreads();
+        const int tile = tile_lo + s_misc[0];
+        if (tile >= tile_hi) break;
+        const int code = a.tile_ng[tile];
+        if (code < 0) {               // whole tile to the generic path
+            if (w == 0) {
+                const int i = tile * 32 + lane;
+                if (i < n) a.worklist[atomicAdd(a.nwork, 1)] = i;
+            }
+            continue;
+        }
+        const int ng = code & 0xffff;
+        const bool interior = (code >> 30) & 1;
+
+        // ---- candidate boxes of the tile (ascending, so particle order is preserved) -----
+        const int *groups = a.tile_groups + (size_t)tile * TL_GROUPS;
+        for (int q = threadIdx.x; q < ng; q += TL_WARPS * 32) s_grp[q] = groups[q];
+        __syncthreads();
+
+        // ---- phase 1: lane = target, bit matrix of the exact predicate at radius R_i ---
+        {
+            const int i = tile * 32 + lane;
+            float xi = 0, yi = 0, zi = 0, R2 = -1.f;
+            if (i < n) {
+                const float4 pi = a.pw[i];
+                xi = pi.x; yi = pi.y; zi = pi.z;
+                const float R = tile_radius(a.hsml_in[i], pi.w, norm, a.bx.box_d);
+                R2 = __fmul_rn(R, R);
+            }
+            for (int q = w; q < ng; q += TL_WARPS) {
+                const int first = s_grp[q] * 32;
+                const int valid = min(32, n - first);            // last box may be short
+                const float4 *cand = a.pw + first;
+                unsigned word = 0;
+#pragma unroll 8
+                for (int b = 0; b < 32; b++) {
+                    const float4 p = __ldg(cand + min(b, valid - 1));   // same address in every lane
+                    bool hit;
+                    if (interior) {
+                        const float dx = __fsub_rn(xi, p.x), dy = __fsub_rn(yi, p.y),
+                                    dz = __fsub_rn(zi, p.z);
+                        hit = sq3_nofma(dx, dy, dz) < R2;
+                    } else {
+                        hit = ngb_pred(xi, yi, zi, p.x, p.y, p.z, R2, box, boxhalf);
+                    }
+                    if (hit) word |= 1u << b;
+                }
+                if (valid < 32) word &= (1u << valid) - 1;
+                s_mask[q * TL_MSTRIDE + lane] = word;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: one warp per target ------------------------------------------------
+        for (;;) {
+            int tsel = 0;
+            if (lane == 0) tsel = atomicAdd(&s_misc[1], 1);
+            tsel = __shfl_sync(FULL_MASK, tsel, 0);
+            if (tsel >= 32) break;
+            const int i = tile * 32 + tsel;
+            if (i >= n) continue;
+
+            const float4 pi = a.pw[i];
+            const float hA = a.hsml_in[i];
+            const float hB = (float)((double)hA * 1.23);                        // sph.c:51
+            const float hi_w = __fmul_rn(pi.w, norm);                           // wvt_relax.c:124
+            const float hsw = (float)((double)hi_w * a.bx.box_d);               // wvt_relax.c:135
+            const float hA2 = __fmul_rn(hA, hA), hB2 = __fmul_rn(hB, hB), hsw2 = __fmul_rn(hsw, hsw);
+            const double A = a.step * (double)hi_w;
+
+            // (1) expand the bit row into a compact, ascending candidate-slot list
+            int nU = 0;
+            for (int base = 0; base < ng; base += 32) {
+                const int q = base + lane;
+                unsigned word = q < ng ? s_mask[q * TL_MSTRIDE + tsel] : 0u;
+                const int c = __popc(word);
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL_MASK, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int off = nU + incl - c;
+                nU += __shfl_sync(FULL_MASK, incl, 31);
+                if (nU <= TL_UCAP) {
+                    while (word) {
+                        const int b = __ffs(word) - 1;
+                        word &= word - 1;
+                        ul[off++] = (unsigned short)(q * 32 + b);
+                    }
+                }
+            }
+            if (nU > TL_UCAP) { hand_back(i); continue; }
+            __syncwarp();
+
+            // (2) classify every hit, build the separation list, sum the displacement
+            int cntA = 0, cntB = 0, cntW = 0;
+            double sx = 0, sy = 0, sz = 0;
+            for (int base = 0; base < nU; base += 32) {
+                const int k = base + lane;
+                const bool live = k < nU;
+                const int slot = live ? ul[k] : 0;
+                const int gidx = s_grp[slot >> 5] * 32 + (slot & 31);
+                const float4 pj = a.pw[gidx];
+                const float xj = pj.x, yj = pj.y, zj = pj.z;
+                float dx = fabsf(__fsub_rn(pi.x, xj)), dy = fabsf(__fsub_rn(pi.y, yj)),
+                      dz = fabsf(__fsub_rn(pi.z, zj));
+                if (dx > boxhalf) dx = __fsub_rn(dx, box);
+                if (dy > boxhalf) dy = __fsub_rn(dy, box);
+                if (dz > boxhalf) dz = __fsub_rn(dz, box);
+                const float r2 = sq3_nofma(dx, dy, dz);                          // tree.c:88
+                const bool inA = live && r2 < hA2, inB = live && r2 < hB2, inW = live && r2 < hsw2;
+                const unsigned mA = __ballot_sync(FULL_MASK, inA), mB = __ballot_sync(FULL_MASK, inB),
+                               mW = __ballot_sync(FULL_MASK, inW);
+                if (MODE & MODE_DENSITY) {
+                    if (inB) {
+                        double r = pair_r(pi.x, pi.y, pi.z, xj, yj, zj, a.bx.box_d, a.bx.boxhalf_d);
+                        if (!inA) r = __longlong_as_double(__double_as_longlong(r) | (1ll << 63));
+                        const int pos = cntB + __popc(mB & lt);
+                        if (pos < TL_LCAP) rl[pos] = r;
+                    }
+                }
+                cntA += __popc(mA);
+                cntB += __popc(mB);
+                if (MODE & MODE_WVT) {
+                    const int wslot = cntW + __popc(mW & lt);
+                    if (inW && wslot < TG_NGBMAX && gidx != i) {                 // tree.c:91, wvt_relax.c:141
+                        double tx, ty, tz;
+                        if (wvt_pair(pi, pj, hi_w, norm, A, a.bx.boxinv_d, tx, ty, tz)) {
+                            sx += tx; sy += ty; sz += tz;
+                            c_pairs++;
+                        }
+                    }
+                }
+                cntW += __popc(mW);
+            }
+            __syncwarp();
+
+            float h = hA, rho = 0, drho = 0;
+            bool ok = true;
+            int cnt = 0;
+            if (MODE & MODE_DENSITY) {
+                // (3) the outer loop of sph.c:36-64, as far as the two prepared radii carry it
+                if (cntA >= TG_DESNNGB) {                    // first search succeeds: Hsml list
+                    if (cntA != cntB) {                      // drop the entries beyond Hsml, in place
+                        int kept = 0;
+                        const int tot = min(cntB, TL_LCAP);
+                        for (int base = 0; base < tot; base += 32) {
+                            const int k = base + lane;
+                            const double r = k < tot ? rl[k] : -1.0;
+                            const bool keep = __double_as_longlong(r) >= 0;
+                            const unsigned mk = __ballot_sync(FULL_MASK, keep);
+                            __syncwarp();
+                            if (keep) rl[kept + __popc(mk & lt)] = r;
+                            kept += __popc(mk);
+                            __syncwarp();
+                        }
+                    }
+                    cnt = cntA; h = hA; c_search += 1;
+                    ok = cntB <= TL_LCAP;            // else list entries were dropped
+                } else if (cntB >= TG_DESNNGB && cntB <= TL_LCAP) {   // second search, 1.23*Hsml
+                    cnt = cntB; h = hB; c_search += 2;
+                } else ok = false;                           // a third search: generic path
+                if (ok) {
+                    __syncwarp();
+                    ok = find_hsml(a, L, cnt, h, rho, drho, c_evals, c_iters);
+                }
+                if (!ok) { hand_back(i); continue; }
+            }
+            c_search += (MODE & MODE_WVT) ? 1 : 0;
+            c_gath += max(cnt, cntW);
+
+            // (4) results
+            if (MODE & MODE_WVT) { sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); }
+            if (lane == 0) {
+                if (MODE & MODE_DENSITY) {                                       // sph.c:66-70
+                    const float q = __fmul_rn(__fdiv_rn(h, __fmul_rn(3.f, rho)), drho);
+                    a.hsml_out[i] = h;
+                    a.rho_out[i] = rho;
+                    a.varh_out[i] = (float)(1.0 / (double)__fadd_rn(1.f, q));
+                }
+                if (MODE & MODE_WVT) {
+                    a.delta[i] = (float)sx;
+                    a.delta[n + i] = (float)sy;
+                    a.delta[2 * (size_t)n + i] = (float)sz;
+                }
+            }
+        }
+    }
+
+    const unsigned long long pairs = warp_sum_u64(c_pairs);
+    if (lane == 0) {
+        atomicAdd(&a.counters[0], c_evals + pairs);
+        atomicAdd(&a.counters[1], c_gath);
+        atomicAdd(&a.counters[2], (unsigned long long)c_search);
+        atomicAdd(&a.counters[3], (unsigned long long)c_iters);
+    }
+}

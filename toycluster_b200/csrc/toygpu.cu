@@ -27,6 +27,7 @@
 #include "model.cuh"
 #include "guess.cuh"
 #include "sph.cuh"
+#include "tile.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -82,10 +83,13 @@ struct tg_ctx {
     double *partial = nullptr;      // block partials
     int npartial = 0;
     double *scal = nullptr;         // [0] vsum, [1] err sum, [2] err max
-    int *flags = nullptr;           // [0] next, [1] status, [2] range_err, [3] n_tied, [4] cold
+    int *flags = nullptr;           // [0] next, [1] status, [2] range_err, [3] n_tied, [4] cold, [5] nwork, [6] next (work list)
     unsigned long long *counters = nullptr;   // 4
     double *gscratch = nullptr;
     int sweep_blocks = 0;
+    int *tile_ng = nullptr, *tile_groups = nullptr, *worklist = nullptr;
+    int tile_blocks = 0;
+    bool use_tiles = true;
 
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     tg_stats stats{};
@@ -142,7 +146,7 @@ extern "C" int tg_destroy(tg_ctx *c)
                     c->hist, c->pw, c->hsml_in, c->rho_model, c->id_s, c->key_lo_s, c->apot_s,
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->cpl,
                     c->ev_level, c->ev_count, c->ev_start, c->guess, c->halos, c->partial, c->scal,
-                    c->flags, c->counters, c->gscratch};
+                    c->flags, c->counters, c->gscratch, c->tile_ng, c->tile_groups, c->worklist};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
@@ -176,7 +180,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     const int n = c->n = cfg->n_gas;
     // equal-sized slices (the last may be short) so one all-gather of `chunk` elements per
     // rank reassembles an array; exchanged arrays are padded to nranks*chunk
-    c->chunk = (n + nranks - 1) / nranks;
+    c->chunk = ((n + nranks - 1) / nranks + 31) / 32 * 32;   // whole 32-target tiles
     c->lo = std::min(n, cfg->rank * c->chunk);
     c->hi = std::min(n, c->lo + c->chunk);
     const size_t npad = (size_t)c->chunk * nranks;
@@ -274,16 +278,36 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
         auto set = [&](const void *f) {
             return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         };
-        CUC(set((const void *)k_sweep<MODE_DENSITY>));
-        CUC(set((const void *)k_sweep<MODE_WVT>));
-        CUC(set((const void *)k_sweep<MODE_WVT_SEQ>));
-        CUC(set((const void *)k_sweep<MODE_DENSITY | MODE_WVT>));
-        CUC(set((const void *)k_sweep<MODE_ROTA>));
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep<MODE_DENSITY | MODE_WVT>,
+        CUC(set((const void *)k_sweep<MODE_DENSITY, false>));
+        CUC(set((const void *)k_sweep<MODE_WVT, false>));
+        CUC(set((const void *)k_sweep<MODE_WVT_SEQ, false>));
+        CUC(set((const void *)k_sweep<MODE_DENSITY | MODE_WVT, false>));
+        CUC(set((const void *)k_sweep<MODE_ROTA, false>));
+        CUC(set((const void *)k_sweep<MODE_DENSITY, true>));
+        CUC(set((const void *)k_sweep<MODE_WVT, true>));
+        CUC(set((const void *)k_sweep<MODE_DENSITY | MODE_WVT, true>));
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep<MODE_DENSITY | MODE_WVT, false>,
                                                           SW_WARPS * 32, smem));
         if (per_sm < 1) per_sm = 1;
     }
     c->sweep_blocks = prop.multiProcessorCount * per_sm;
+    {
+        auto set = [&](const void *f) {
+            return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM);
+        };
+        CUC(set((const void *)k_sweep_tile<MODE_DENSITY>));
+        CUC(set((const void *)k_sweep_tile<MODE_WVT>));
+        CUC(set((const void *)k_sweep_tile<MODE_DENSITY | MODE_WVT>));
+        int tile_per_sm = 1;
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&tile_per_sm, k_sweep_tile<MODE_DENSITY | MODE_WVT>,
+                                                          TL_WARPS * 32, TL_SMEM));
+        if (tile_per_sm < 1) tile_per_sm = 1;
+        c->tile_blocks = prop.multiProcessorCount * tile_per_sm;
+    }
+    CUC(dmalloc(&c->tile_ng, (size_t)t.lvl_n[0]));
+    CUC(dmalloc(&c->tile_groups, (size_t)t.lvl_n[0] * TL_GROUPS));
+    CUC(dmalloc(&c->worklist, (size_t)n));
+    c->use_tiles = getenv("TOYGPU_NO_TILES") == nullptr;
     CUC(dmalloc(&c->gscratch, (size_t)c->sweep_blocks * SW_WARPS * TG_NGBMAX));
     CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
@@ -379,6 +403,7 @@ static int reset_counters(tg_ctx *c)
 {
     CU(cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned long long), c->stream));
     CU(cudaMemsetAsync(c->flags + 1, 0, sizeof(int), c->stream));   // sweep status
+    CU(cudaMemsetAsync(c->flags + 5, 0, sizeof(int), c->stream));   // handed-back count
     c->launches = 0;
     return TG_OK;
 }
@@ -486,16 +511,51 @@ static SweepArgs sweep_args(tg_ctx *c, double step)
     a.varh_in = c->varh;
     a.apot = c->apot;
     a.bfld = c->bfld;
+    a.worklist = c->worklist;
+    a.nwork = c->flags + 5;
+    a.tile_ng = c->tile_ng;
+    a.tile_groups = c->tile_groups;
     return a;
+}
+
+// Generic (v1) sweep over [lo, hi).
+template <int MODE> static int launch_generic(tg_ctx *c, SweepArgs a)
+{
+    const size_t smem = (size_t)SW_WARPS * SW_LCAP * sizeof(double);
+    CU(cudaMemsetAsync(c->flags, 0, sizeof(int), c->stream));       // work counter
+    a.next = c->flags;
+    k_sweep<MODE, false><<<c->sweep_blocks, SW_WARPS * 32, smem, c->stream>>>(a);
+    LAUNCH_CHECK();
+    return TG_OK;
+}
+
+// Tile (v2) sweep, then the generic kernel on whatever the tiles handed back.
+template <int MODE> static int launch_tiled(tg_ctx *c, SweepArgs a)
+{
+    const size_t smem = (size_t)SW_WARPS * SW_LCAP * sizeof(double);
+    const int tile_lo = c->lo / 32, tile_hi = (c->hi + 31) / 32;
+    if (tile_hi <= tile_lo) return TG_OK;
+    CU(cudaMemsetAsync(c->flags, 0, sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->flags + 5, 0, 2 * sizeof(int), c->stream));
+    k_tile_walk<<<cdiv((long long)(tile_hi - tile_lo) * 32, 256), 256, 0, c->stream>>>(
+        c->bvh, c->box, c->pw, c->hsml_in, c->scal, tile_lo, tile_hi, c->tile_ng, c->tile_groups);
+    LAUNCH_CHECK();
+    a.next = c->flags;
+    k_sweep_tile<MODE><<<c->tile_blocks, TL_WARPS * 32, TL_SMEM, c->stream>>>(a, tile_lo, tile_hi);
+    LAUNCH_CHECK();
+    a.next = c->flags + 6;
+    k_sweep<MODE, true><<<c->sweep_blocks, SW_WARPS * 32, smem, c->stream>>>(a);
+    LAUNCH_CHECK();
+    return TG_OK;
 }
 
 template <int MODE> static int launch_sweep(tg_ctx *c, const SweepArgs &a)
 {
-    const size_t smem = (size_t)SW_WARPS * SW_LCAP * sizeof(double);
-    CU(cudaMemsetAsync(c->flags, 0, sizeof(int), c->stream));       // work counter
-    k_sweep<MODE><<<c->sweep_blocks, SW_WARPS * 32, smem, c->stream>>>(a);
-    LAUNCH_CHECK();
-    return TG_OK;
+    constexpr bool tileable = MODE == MODE_DENSITY || MODE == MODE_WVT || MODE == (MODE_DENSITY | MODE_WVT);
+    if constexpr (tileable) {
+        if (c->use_tiles && !c->any_cold) return launch_tiled<MODE>(c, a);
+    }
+    return launch_generic<MODE>(c, a);
 }
 
 static int check_flags(tg_ctx *c)
@@ -560,8 +620,11 @@ static int move_pass(tg_ctx *c)
 static int finish_stats(tg_ctx *c, bool have_sweep_events)
 {
     unsigned long long h[4];
+    int nwork = 0;
     CU(cudaMemcpyAsync(h, c->counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&nwork, c->flags + 5, sizeof nwork, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    c->stats.handed_back = (unsigned long long)nwork;
     c->stats.pair_evals = h[0];
     c->stats.gathered = h[1];
     c->stats.searches = h[2];
@@ -850,6 +913,19 @@ extern "C" int tg_guess_hsml(tg_ctx *c, float *out)
     LAUNCH_CHECK();
     CU(cudaMemcpyAsync(out, c->guess, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return TG_OK;
+}
+
+// Diagnostics: candidate-box count per tile of the last tiled sweep (negative = handed back).
+extern "C" int tg_debug_tile_counts(tg_ctx *c, int *out, int *ntiles)
+{
+    if (!c || !ntiles) return TG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    *ntiles = c->bvh.lvl_n[0];
+    if (out) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(out, c->tile_ng, sizeof(int) * c->bvh.lvl_n[0], cudaMemcpyDeviceToHost));
+    }
     return TG_OK;
 }
 
