@@ -28,17 +28,24 @@
 #include "sph.cuh"
 
 #define TL_WARPS 8
-#define TL_GROUPS 288                    // candidate boxes per tile (median ~150 at 1 M)
-#define TL_UCAP 896                      // hits within R_i kept per target
-#define TL_LCAP 640                      // density list entries per target
+#ifndef TL_GROUPS
+#define TL_GROUPS 224                    // candidate boxes per tile (median ~150 at 1 M)
+#endif
+#ifndef TL_CAP
+#define TL_CAP 704                       // hits within R_i / density list entries per target
+#endif
+#define TL_UCAP TL_CAP
+#define TL_LCAP TL_CAP
 #define TL_MSTRIDE 33                    // bit-matrix row stride (words), odd => no bank conflicts
 
-// shared memory layout (bytes): bit matrix, box list, per-warp lists
+// Shared memory layout (bytes): bit matrix, box list, one list region per warp.  The region
+// holds TL_CAP doubles (the separation list); the 16-bit hit list lives in its last quarter:
+// entry k of the hit list is dead once batch k/32 has been read, and the separation list
+// can only have grown to 8*(k+32) <= 6*TL_CAP + 2*(k+32) bytes by then.
 #define TL_OFF_MASK 0
 #define TL_OFF_GRP (TL_OFF_MASK + TL_GROUPS * TL_MSTRIDE * 4)
 #define TL_OFF_RL (TL_OFF_GRP + TL_GROUPS * 4)
-#define TL_OFF_UL (TL_OFF_RL + TL_WARPS * TL_LCAP * 8)
-#define TL_OFF_MISC (TL_OFF_UL + TL_WARPS * TL_UCAP * 2)
+#define TL_OFF_MISC (TL_OFF_RL + TL_WARPS * TL_CAP * 8)
 #define TL_SMEM (TL_OFF_MISC + 64)
 
 // Periodic gap^2 between two boxes (centre/half-width form).
@@ -123,7 +130,7 @@ struct TileList {     // density list: r as double; the sign bit marks "outside 
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TL_WARPS * 32, 2) k_sweep_tile(const SweepArgs a, int tile_lo,
+__global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs a, int tile_lo,
                                                                    int tile_hi)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -134,8 +141,8 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 2) k_sweep_tile(const SweepArgs
     const int lane = lane_id();
     const int w = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1;
-    double *rl = (double *)(smem + TL_OFF_RL) + w * TL_LCAP;
-    unsigned short *ul = (unsigned short *)(smem + TL_OFF_UL) + w * TL_UCAP;
+    double *rl = (double *)(smem + TL_OFF_RL) + w * TL_CAP;
+    unsigned short *ul = (unsigned short *)(rl + (TL_CAP / 4) * 3);   // last quarter of the region
     TileList L{rl};
 
     const float norm = (float)pow(TG_DESNNGB / *a.vsum / K_FOURPITHIRD, 1.0 / 3.0);   // wvt_relax.c:120
@@ -181,25 +188,37 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 2) k_sweep_tile(const SweepArgs
                 const float R = tile_radius(a.hsml_in[i], pi.w, norm, a.bx.box_d);
                 R2 = __fmul_rn(R, R);
             }
+            // The bit only has to be a SUPERSET of the exact predicate (phase 2 re-evaluates
+            // every hit with the FMA-free arithmetic of tree.c:88), so the sum of squares is
+            // contracted to two FMAs and compared against a radius inflated by 1e-6.
+            const float R2p = R2 * 1.000001f;
+            auto test = [&](const float4 p) -> bool {
+                float dx = __fsub_rn(xi, p.x), dy = __fsub_rn(yi, p.y), dz = __fsub_rn(zi, p.z);
+                if (!interior) {
+                    dx = fabsf(dx); dy = fabsf(dy); dz = fabsf(dz);
+                    if (dx > boxhalf) dx = __fsub_rn(dx, box);
+                    if (dy > boxhalf) dy = __fsub_rn(dy, box);
+                    if (dz > boxhalf) dz = __fsub_rn(dz, box);
+                }
+                return fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < R2p;
+            };
             for (int q = w; q < ng; q += TL_WARPS) {
                 const int first = s_grp[q] * 32;
-                const int valid = min(32, n - first);            // last box may be short
-                const float4 *cand = a.pw + first;
+                const float4 *cand = a.pw + first;      // same address in every lane: broadcast
                 unsigned word = 0;
-#pragma unroll 8
-                for (int b = 0; b < 32; b++) {
-                    const float4 p = __ldg(cand + min(b, valid - 1));   // same address in every lane
-                    bool hit;
-                    if (interior) {
-                        const float dx = __fsub_rn(xi, p.x), dy = __fsub_rn(yi, p.y),
-                                    dz = __fsub_rn(zi, p.z);
-                        hit = sq3_nofma(dx, dy, dz) < R2;
-                    } else {
-                        hit = ngb_pred(xi, yi, zi, p.x, p.y, p.z, R2, box, boxhalf);
+                if (first + 32 <= n) {
+#pragma unroll 1
+                    for (int c = 0; c < 32; c += 8) {    // 8 independent loads in flight
+                        unsigned sub = 0;
+#pragma unroll
+                        for (int b = 0; b < 8; b++)
+                            if (test(__ldg(cand + c + b))) sub |= 1u << b;
+                        word |= sub << c;
                     }
-                    if (hit) word |= 1u << b;
+                } else {                                 // the last box may be short
+                    for (int b = 0; b < n - first; b++)
+                        if (test(__ldg(cand + b))) word |= 1u << b;
                 }
-                if (valid < 32) word &= (1u << valid) - 1;
                 s_mask[q * TL_MSTRIDE + lane] = word;
             }
         }
@@ -254,6 +273,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 2) k_sweep_tile(const SweepArgs
                 const int k = base + lane;
                 const bool live = k < nU;
                 const int slot = live ? ul[k] : 0;
+                __syncwarp();                       // hit list batch read before the region is reused
                 const int gidx = s_grp[slot >> 5] * 32 + (slot & 31);
                 const float4 pj = a.pw[gidx];
                 const float xj = pj.x, yj = pj.y, zj = pj.z;
