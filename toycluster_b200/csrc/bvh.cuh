@@ -15,9 +15,10 @@
 #pragma once
 #include "common.cuh"
 
-// level 0: one warp per group of 32 particles
+// level 0: one warp per group of 32 particles; also the boxes of its four runs of 8
 __global__ void k_bvh_leaves(int n, const float4 *__restrict__ pw, int n0, float pad,
-                             float *cx, float *cy, float *cz, float *hx, float *hy, float *hz)
+                             float *cx, float *cy, float *cz, float *hx, float *hy, float *hz,
+                             float *scx, float *scy, float *scz, float *shx, float *shy, float *shz)
 {
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= n0) return;
@@ -29,13 +30,19 @@ __global__ void k_bvh_leaves(int n, const float4 *__restrict__ pw, int n0, float
         lx = ux = p.x; ly = uy = p.y; lz = uz = p.z;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 1; o < 32; o <<= 1) {
         lx = fminf(lx, __shfl_xor_sync(FULL_MASK, lx, o));
         ly = fminf(ly, __shfl_xor_sync(FULL_MASK, ly, o));
         lz = fminf(lz, __shfl_xor_sync(FULL_MASK, lz, o));
         ux = fmaxf(ux, __shfl_xor_sync(FULL_MASK, ux, o));
         uy = fmaxf(uy, __shfl_xor_sync(FULL_MASK, uy, o));
         uz = fmaxf(uz, __shfl_xor_sync(FULL_MASK, uz, o));
+        if (o == 4 && (lane & 7) == 0) {      // reduced over aligned runs of 8 lanes
+            const int s = 4 * g + (lane >> 3);
+            scx[s] = 0.5f * (lx + ux); shx[s] = 0.5f * (ux - lx) + pad;
+            scy[s] = 0.5f * (ly + uy); shy[s] = 0.5f * (uy - ly) + pad;
+            scz[s] = 0.5f * (lz + uz); shz[s] = 0.5f * (uz - lz) + pad;
+        }
     }
     if (lane == 0) {
         cx[g] = 0.5f * (lx + ux); hx[g] = 0.5f * (ux - lx) + pad;

@@ -29,6 +29,8 @@ struct Bvh {
     int lvl_off[MAX_LEVELS];  // offset of each level in the SoA arrays
     const float *cx, *cy, *cz;   // box centres
     const float *hx, *hy, *hz;   // box half-widths (already inflated for rounding)
+    // four sub-boxes (runs of 8 particles) per level-0 box, index 4*g + s; used by the tile walk
+    const float *scx, *scy, *scz, *shx, *shy, *shz;
 };
 
 struct Box {

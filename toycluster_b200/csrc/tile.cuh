@@ -28,23 +28,27 @@
 #include "sph.cuh"
 
 #define TL_WARPS 8
-#ifndef TL_GROUPS
-#define TL_GROUPS 224                    // candidate boxes per tile (median ~150 at 1 M)
+#ifndef TL_ENT
+#define TL_ENT 256                       // candidate level-0 boxes per tile (global list entries)
+#endif
+#ifndef TL_RUNS
+#define TL_RUNS 512                      // candidate runs of 8 particles per tile
 #endif
 #ifndef TL_CAP
 #define TL_CAP 704                       // hits within R_i / density list entries per target
 #endif
+#define TL_WORDS (TL_RUNS / 4)           // bit-matrix words per target (4 runs = 32 candidates)
 #define TL_UCAP TL_CAP
 #define TL_LCAP TL_CAP
 #define TL_MSTRIDE 33                    // bit-matrix row stride (words), odd => no bank conflicts
 
-// Shared memory layout (bytes): bit matrix, box list, one list region per warp.  The region
+// Shared memory layout (bytes): bit matrix, run list, one list region per warp.  The region
 // holds TL_CAP doubles (the separation list); the 16-bit hit list lives in its last quarter:
 // entry k of the hit list is dead once batch k/32 has been read, and the separation list
 // can only have grown to 8*(k+32) <= 6*TL_CAP + 2*(k+32) bytes by then.
 #define TL_OFF_MASK 0
-#define TL_OFF_GRP (TL_OFF_MASK + TL_GROUPS * TL_MSTRIDE * 4)
-#define TL_OFF_RL (TL_OFF_GRP + TL_GROUPS * 4)
+#define TL_OFF_RUN (TL_OFF_MASK + TL_WORDS * TL_MSTRIDE * 4)
+#define TL_OFF_RL (TL_OFF_RUN + TL_RUNS * 4)
 #define TL_OFF_MISC (TL_OFF_RL + TL_WARPS * TL_CAP * 8)
 #define TL_SMEM (TL_OFF_MISC + 64)
 
@@ -72,9 +76,12 @@ static __device__ __forceinline__ float tile_radius(float hA, float hw_raw, floa
     return fmaxf(hB, hsw);
 }
 
-// tile_ng[tile] = number of candidate boxes (bit 30 set: no target of the tile can see a
-// periodic image, so phase 1 may skip the wrap), or -1 when the tile must take the generic
-// path.  One warp per tile.
+// Candidate list of a tile.  tile_ng[tile] = number of entries (bit 30 set: no target of the
+// tile can see a periodic image, so phase 1 may skip the wrap), or <= -1 when the tile must
+// take the generic path.  An entry is (level-0 box << 4) | mask of its four 8-particle runs
+// that lie within reach of the tile.  "Reach" is tested run against run: the tile's own four
+// sub-boxes, each with the largest radius of its 8 targets, against the candidate's four.
+// One warp per tile.
 __global__ void k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw,
                             const float *__restrict__ hsml_in, const double *__restrict__ vsum,
                             int tile_lo, int tile_hi, int *__restrict__ tile_ng,
@@ -93,8 +100,12 @@ __global__ void k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw,
         cold = hA == 0;
         R = tile_radius(hA, pw[i].w, norm, bx.box_d);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) R = fmaxf(R, __shfl_xor_sync(FULL_MASK, R, o));
+    R = fmaxf(R, __shfl_xor_sync(FULL_MASK, R, 1));
+    R = fmaxf(R, __shfl_xor_sync(FULL_MASK, R, 2));
+    R = fmaxf(R, __shfl_xor_sync(FULL_MASK, R, 4));
+    const float Rsub = R;                       // max over this lane's run of 8 targets
+    R = fmaxf(R, __shfl_xor_sync(FULL_MASK, R, 8));
+    R = fmaxf(R, __shfl_xor_sync(FULL_MASK, R, 16));
     if (__any_sync(FULL_MASK, cold) || !(R < bx.boxhalf_f)) {
         if (lane == 0) tile_ng[tile] = -1;
         return;
@@ -102,24 +113,41 @@ __global__ void k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw,
     const float ax = t.cx[tile], ay = t.cy[tile], az = t.cz[tile];
     const float ahx = t.hx[tile], ahy = t.hy[tile], ahz = t.hz[tile];
     const float R2 = R * R * 1.00001f;
-    int ng = 0;
-    int *out = tile_groups + (size_t)tile * TL_GROUPS;
+    // lane = (tile run a, candidate run b): a = lane >> 2 (lanes 0..15 used), b = lane & 3
+    const int ra = (lane >> 2) & 3, rb = lane & 3;
+    const int sa = 4 * tile + ra;
+    const float tx = t.scx[sa], ty = t.scy[sa], tz = t.scz[sa];
+    const float thx = t.shx[sa], thy = t.shy[sa], thz = t.shz[sa];
+    const float Ra = __shfl_sync(FULL_MASK, Rsub, ra * 8);
+    const float Ra2 = Ra * Ra * 1.00001f;
+
+    int ng = 0, nruns = 0;
+    int *out = tile_groups + (size_t)tile * TL_ENT;
     bvh_walk_pred(t, [&](int o) -> bool {
         return box_box_dist2(ax, ay, az, ahx, ahy, ahz, t.cx[o], t.cy[o], t.cz[o], t.hx[o], t.hy[o],
                              t.hz[o], bx.box_f, bx.boxhalf_f) <= R2;
     }, [&](int g) -> bool {
-        if (ng < TL_GROUPS && lane == 0) out[ng] = g;
-        ng++;
+        const int sb = 4 * g + rb;
+        const bool near = lane < 16 &&
+            box_box_dist2(tx, ty, tz, thx, thy, thz, t.scx[sb], t.scy[sb], t.scz[sb], t.shx[sb],
+                          t.shy[sb], t.shz[sb], bx.box_f, bx.boxhalf_f) <= Ra2;
+        unsigned m = __ballot_sync(FULL_MASK, near);
+        m = (m | (m >> 4) | (m >> 8) | (m >> 12)) & 0xfu;
+        if (m) {
+            if (ng < TL_ENT && lane == 0) out[ng] = (g << 4) | (int)m;
+            ng++;
+            nruns += __popc(m);
+        }
         return ng < 8192;        // keep counting past the cap: the count feeds diagnostics
     });
     if (lane == 0) {
-        if (ng > TL_GROUPS) tile_ng[tile] = -ng;
+        if (ng > TL_ENT || nruns > TL_RUNS) tile_ng[tile] = -max(nruns, 2);
         else {
             const float m = R * 1.0001f;   // margin: a wrapped pair must stay a miss after rounding
             const bool interior = ax - ahx - m >= 0 && ax + ahx + m <= bx.box_f &&
                                   ay - ahy - m >= 0 && ay + ahy + m <= bx.box_f &&
                                   az - ahz - m >= 0 && az + ahz + m <= bx.box_f;
-            tile_ng[tile] = ng | (interior ? (1 << 30) : 0);
+            tile_ng[tile] = ng | (nruns << 12) | (interior ? (1 << 30) : 0);
         }
     }
 }
@@ -135,7 +163,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
 {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned *s_mask = (unsigned *)(smem + TL_OFF_MASK);
-    int *s_grp = (int *)(smem + TL_OFF_GRP);
+    int *s_run = (int *)(smem + TL_OFF_RUN);        // first particle of each candidate run
     int *s_misc = (int *)(smem + TL_OFF_MISC);       // [0] tile, [1] next target
 
     const int lane = lane_id();
@@ -170,12 +198,30 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
             }
             continue;
         }
-        const int ng = code & 0xffff;
+        const int nent = code & 0xfff, nruns = (code >> 12) & 0xffff;
+        const int ng = (nruns + 3) >> 2;           // bit-matrix words
         const bool interior = (code >> 30) & 1;
 
-        // ---- candidate boxes of the tile (ascending, so particle order is preserved) -----
-        const int *groups = a.tile_groups + (size_t)tile * TL_GROUPS;
-        for (int q = threadIdx.x; q < ng; q += TL_WARPS * 32) s_grp[q] = groups[q];
+        // ---- candidate runs of the tile (ascending, so particle order is preserved) ------
+        if (w == 0) {
+            const int *ent = a.tile_groups + (size_t)tile * TL_ENT;
+            int base = 0;
+            for (int e0 = 0; e0 < nent; e0 += 32) {
+                const int e = e0 + lane;
+                const int v = e < nent ? ent[e] : 0;
+                const int c = __popc(v & 0xf);
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(FULL_MASK, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                int off = base + incl - c;
+                for (int b = 0; b < 4; b++)
+                    if (v & (1 << b)) s_run[off++] = (v >> 4) * 32 + 8 * b;
+                base += __shfl_sync(FULL_MASK, incl, 31);
+            }
+        }
         __syncthreads();
 
         // ---- phase 1: lane = target, bit matrix of the exact predicate at radius R_i ---
@@ -203,21 +249,23 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 return fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < R2p;
             };
             for (int q = w; q < ng; q += TL_WARPS) {
-                const int first = s_grp[q] * 32;
-                const float4 *cand = a.pw + first;      // same address in every lane: broadcast
                 unsigned word = 0;
-                if (first + 32 <= n) {
 #pragma unroll 1
-                    for (int c = 0; c < 32; c += 8) {    // 8 independent loads in flight
-                        unsigned sub = 0;
+                for (int c = 0; c < 4; c++) {            // four runs of 8 candidates per word
+                    const int r8 = 4 * q + c;
+                    if (r8 >= nruns) break;
+                    const int first = s_run[r8];
+                    const float4 *cand = a.pw + first;   // same address in every lane: broadcast
+                    unsigned sub = 0;
+                    if (first + 8 <= n) {
 #pragma unroll
-                        for (int b = 0; b < 8; b++)
-                            if (test(__ldg(cand + c + b))) sub |= 1u << b;
-                        word |= sub << c;
+                        for (int b = 0; b < 8; b++)      // 8 independent loads in flight
+                            if (test(__ldg(cand + b))) sub |= 1u << b;
+                    } else {                             // the last run may be short
+                        for (int b = 0; b < n - first; b++)
+                            if (test(__ldg(cand + b))) sub |= 1u << b;
                     }
-                } else {                                 // the last box may be short
-                    for (int b = 0; b < n - first; b++)
-                        if (test(__ldg(cand + b))) word |= 1u << b;
+                    word |= sub << (8 * c);
                 }
                 s_mask[q * TL_MSTRIDE + lane] = word;
             }
@@ -274,7 +322,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 const bool live = k < nU;
                 const int slot = live ? ul[k] : 0;
                 __syncwarp();                       // hit list batch read before the region is reused
-                const int gidx = s_grp[slot >> 5] * 32 + (slot & 31);
+                const int gidx = s_run[slot >> 3] + (slot & 7);
                 const float4 pj = a.pw[gidx];
                 const float xj = pj.x, yj = pj.y, zj = pj.z;
                 float dx = fabsf(__fsub_rn(pi.x, xj)), dy = fabsf(__fsub_rn(pi.y, yj)),

@@ -69,7 +69,7 @@ struct tg_ctx {
 
     // index
     Bvh bvh{};
-    float *bvh_mem = nullptr;
+    float *bvh_mem = nullptr, *sub_mem = nullptr;
     int bvh_total = 0;
 
     // cold start
@@ -144,7 +144,7 @@ extern "C" int tg_destroy(tg_ctx *c)
     cudaSetDevice(c->cfg.device);
     void *ptrs[] = {c->posh, c->id, c->apot, c->stage, c->key_hi, c->key_lo, c->key_tmp, c->idx, c->idx_tmp,
                     c->hist, c->pw, c->hsml_in, c->rho_model, c->id_s, c->key_lo_s, c->apot_s,
-                    c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->cpl,
+                    c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->sub_mem, c->cpl,
                     c->ev_level, c->ev_count, c->ev_start, c->guess, c->halos, c->partial, c->scal,
                     c->flags, c->counters, c->gscratch, c->tile_ng, c->tile_groups, c->worklist};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -253,6 +253,12 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     t.cx = c->bvh_mem; t.cy = c->bvh_mem + total; t.cz = c->bvh_mem + 2 * (size_t)total;
     t.hx = c->bvh_mem + 3 * (size_t)total; t.hy = c->bvh_mem + 4 * (size_t)total;
     t.hz = c->bvh_mem + 5 * (size_t)total;
+    {
+        const size_t ns = (size_t)4 * t.lvl_n[0];
+        CUC(dmalloc(&c->sub_mem, 6 * ns));
+        t.scx = c->sub_mem; t.scy = c->sub_mem + ns; t.scz = c->sub_mem + 2 * ns;
+        t.shx = c->sub_mem + 3 * ns; t.shy = c->sub_mem + 4 * ns; t.shz = c->sub_mem + 5 * ns;
+    }
 
     CUC(dmalloc(&c->cpl, n));
     CUC(dmalloc(&c->ev_level, n));
@@ -305,7 +311,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
         c->tile_blocks = prop.multiProcessorCount * tile_per_sm;
     }
     CUC(dmalloc(&c->tile_ng, (size_t)t.lvl_n[0]));
-    CUC(dmalloc(&c->tile_groups, (size_t)t.lvl_n[0] * TL_GROUPS));
+    CUC(dmalloc(&c->tile_groups, (size_t)t.lvl_n[0] * TL_ENT));
     CUC(dmalloc(&c->worklist, (size_t)n));
     c->use_tiles = getenv("TOYGPU_NO_TILES") == nullptr;
     CUC(dmalloc(&c->gscratch, (size_t)c->sweep_blocks * SW_WARPS * TG_NGBMAX));
@@ -457,7 +463,8 @@ static int prepare_index(tg_ctx *c)
     const size_t S = c->bvh_total;
     const float pad = 4e-7f * c->box.box_f;
     k_bvh_leaves<<<cdiv((long long)t.lvl_n[0] * 32, T), T, 0, c->stream>>>(
-        n, c->pw, t.lvl_n[0], pad, m, m + S, m + 2 * S, m + 3 * S, m + 4 * S, m + 5 * S);
+        n, c->pw, t.lvl_n[0], pad, m, m + S, m + 2 * S, m + 3 * S, m + 4 * S, m + 5 * S,
+        (float *)t.scx, (float *)t.scy, (float *)t.scz, (float *)t.shx, (float *)t.shy, (float *)t.shz);
     LAUNCH_CHECK();
     for (int l = 1; l <= t.top; l++) {
         const int oc = t.lvl_off[l - 1], op = t.lvl_off[l];
