@@ -50,7 +50,7 @@
 #define TL_OFF_RUN (TL_OFF_MASK + TL_WORDS * TL_MSTRIDE * 4)
 #define TL_OFF_RL (TL_OFF_RUN + TL_RUNS * 4)
 #define TL_OFF_MISC (TL_OFF_RL + TL_WARPS * TL_CAP * 8)
-#define TL_SMEM (TL_OFF_MISC + 64)
+#define TL_SMEM (TL_OFF_MISC + 64)             // misc: 2 ints, 32-byte bit-index table at +16
 
 // Periodic gap^2 between two boxes (centre/half-width form).
 static __device__ __forceinline__ float box_box_dist2(float ax, float ay, float az, float ahx,
@@ -175,7 +175,13 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
 
     const float norm = (float)pow(TG_DESNNGB / *a.vsum / K_FOURPITHIRD, 1.0 / 3.0);   // wvt_relax.c:120
     const float box = a.bx.box_f, boxhalf = a.bx.boxhalf_f;
+    const float binv_hi = (float)a.bx.boxinv_d, binv_lo = (float)(a.bx.boxinv_d - (double)binv_hi);
     const int n = a.t.n;
+
+    // lowest-set-bit index by de Bruijn multiplication + a 32-byte table: the expansion loop
+    // below would otherwise issue BREV+FLO on the XU pipe for every hit
+    unsigned char *s_bit = (unsigned char *)(s_misc + 4);
+    if (threadIdx.x < 32) s_bit[(0x077CB531u << threadIdx.x) >> 27] = (unsigned char)threadIdx.x;
 
     unsigned long long c_evals = 0, c_gath = 0, c_pairs = 0;
     unsigned c_search = 0, c_iters = 0;
@@ -305,9 +311,9 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 nU += __shfl_sync(FULL_MASK, incl, 31);
                 if (nU <= TL_UCAP) {
                     while (word) {
-                        const int b = __ffs(word) - 1;
-                        word &= word - 1;
-                        ul[off++] = (unsigned short)(q * 32 + b);
+                        const unsigned low = word & (0u - word);
+                        word ^= low;
+                        ul[off++] = (unsigned short)(q * 32 + s_bit[(low * 0x077CB531u) >> 27]);
                     }
                 }
             }
@@ -315,8 +321,9 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
             __syncwarp();
 
             // (2) classify every hit, build the separation list, sum the displacement
-            int cntA = 0, cntB = 0, cntW = 0;
-            double sx = 0, sy = 0, sz = 0;
+            int cntA = 0, cntB = 0, cntW = 0;      // cntA, cntW: per-lane until reduced below
+            float sx = 0, sy = 0, sz = 0;
+            const float Af = (float)A;
             for (int base = 0; base < nU; base += 32) {
                 const int k = base + lane;
                 const bool live = k < nU;
@@ -332,8 +339,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 if (dz > boxhalf) dz = __fsub_rn(dz, box);
                 const float r2 = sq3_nofma(dx, dy, dz);                          // tree.c:88
                 const bool inA = live && r2 < hA2, inB = live && r2 < hB2, inW = live && r2 < hsw2;
-                const unsigned mA = __ballot_sync(FULL_MASK, inA), mB = __ballot_sync(FULL_MASK, inB),
-                               mW = __ballot_sync(FULL_MASK, inW);
+                const unsigned mB = __ballot_sync(FULL_MASK, inB);
                 if (MODE & MODE_DENSITY) {
                     if (inB) {
                         double r = pair_r(pi.x, pi.y, pi.z, xj, yj, zj, a.bx.box_d, a.bx.boxhalf_d);
@@ -342,19 +348,24 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                         if (pos < TL_LCAP) rl[pos] = r;
                     }
                 }
-                cntA += __popc(mA);
+                cntA += inA;
                 cntB += __popc(mB);
+                cntW += inW;
                 if (MODE & MODE_WVT) {
-                    const int wslot = cntW + __popc(mW & lt);
-                    if (inW && wslot < TG_NGBMAX && gidx != i) {                 // tree.c:91, wvt_relax.c:141
-                        double tx, ty, tz;
-                        if (wvt_pair(pi, pj, hi_w, norm, A, a.bx.boxinv_d, tx, ty, tz)) {
+                    // nU <= TL_CAP < NGBMAX: the list cut of tree.c:91 cannot bite here
+                    if (inW && gidx != i) {                                      // wvt_relax.c:141
+                        float tx, ty, tz;
+                        if (wvt_pair_fast(pi, pj, hi_w, norm, Af, binv_hi, binv_lo, tx, ty, tz)) {
                             sx += tx; sy += ty; sz += tz;
                             c_pairs++;
                         }
                     }
                 }
-                cntW += __popc(mW);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                cntA += __shfl_xor_sync(FULL_MASK, cntA, o);
+                cntW += __shfl_xor_sync(FULL_MASK, cntW, o);
             }
             __syncwarp();
 
@@ -393,7 +404,8 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
             c_gath += max(cnt, cntW);
 
             // (4) results
-            if (MODE & MODE_WVT) { sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); }
+            double dsx = 0, dsy = 0, dsz = 0;
+            if (MODE & MODE_WVT) { dsx = warp_sum((double)sx); dsy = warp_sum((double)sy); dsz = warp_sum((double)sz); }
             if (lane == 0) {
                 if (MODE & MODE_DENSITY) {                                       // sph.c:66-70
                     const float q = __fmul_rn(__fdiv_rn(h, __fmul_rn(3.f, rho)), drho);
@@ -402,9 +414,9 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                     a.varh_out[i] = (float)(1.0 / (double)__fadd_rn(1.f, q));
                 }
                 if (MODE & MODE_WVT) {
-                    a.delta[i] = (float)sx;
-                    a.delta[n + i] = (float)sy;
-                    a.delta[2 * (size_t)n + i] = (float)sz;
+                    a.delta[i] = (float)dsx;
+                    a.delta[n + i] = (float)dsy;
+                    a.delta[2 * (size_t)n + i] = (float)dsz;
                 }
             }
         }
