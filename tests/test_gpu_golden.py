@@ -1,0 +1,149 @@
+"""GPU parity against the committed golden fixtures (no reference needed at run time), plus
+the properties that do not depend on size: tile path == generic path, rank slices == one rank,
+AoS records travel with their particle."""
+import os
+
+import numpy as np
+import pytest
+
+import toycluster_b200 as tc
+from toycluster_b200 import workloads
+from toycluster_b200.dist import rank_slice
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "merger_4096.npz"))
+
+
+def _ctx(gold, **kw):
+    return tc.HotPath(int(gold["n_gas"]), float(gold["boxsize"]), float(gold["mpart_gas"]),
+                      float(gold["mtotal"]), gold["halo_table"], **kw)
+
+
+def test_golden_sort_guess_neighbours(gold):
+    g = _ctx(gold)
+    g.upload(gold["pos0"])
+    assert np.array_equal(g.sort(), gold["sort_id"])
+    assert np.array_equal(g.guess_hsml(), gold["guess2"])
+    off = 0
+    for i, h, cnt in gold["ngb_queries"]:
+        want = gold["ngb_lists"][off:off + int(cnt)]
+        off += int(cnt)
+        assert np.array_equal(g.find_ngb(int(i), np.float32(h)), want), (i, h)
+
+
+def test_golden_iterations_sequential(gold):
+    g = _ctx(gold, flags=tc.WVT_SEQUENTIAL)
+    g.upload(gold["pos0"])
+    for it in range(4):
+        g.wvt_iteration(float(gold["log"][it + 1][4]) if it + 1 < len(gold["log"]) else 0.0085)
+        o = g.download()
+        hw, dl = g.wvt_scratch()
+        assert np.array_equal(o["id"], gold[f"it{it}_id"])
+        for k in ("hsml", "rho", "varhsml", "rho_model", "pos"):
+            assert np.array_equal(o[k], gold[f"it{it}_{k}"]), (it, k)
+        assert np.array_equal(hw, gold[f"it{it}_hw"]) and np.array_equal(dl, gold[f"it{it}_delta"])
+        if it == 2:
+            break
+
+
+def test_golden_final_density_and_rotA(gold):
+    """Find_sph_quantities + Bfld_from_rotA_SPH as main.c:54-56 calls them."""
+    g = _ctx(gold)
+    g.upload(gold["it3_pos"], gold["it3_hsml"])
+    g.find_sph_quantities()
+    o = g.download()
+    assert np.array_equal(gold["it3_id"][o["id"]], gold["final_id"])
+    for k in ("pos", "hsml", "rho", "varhsml"):
+        assert np.array_equal(o[k], gold[f"final_{k}"]), k
+    g.set_apot(gold["final_apot"])           # current (Peano) order, like magnetic_field.c:33-69
+    g.bfld_from_rotA_sph()
+    b = g.download(bfld=True)["bfld"]
+    want = gold["final_bfld"]
+    rel = np.abs(b.astype(np.float64) - want) / np.maximum(np.abs(want), np.abs(want).max() * 1e-6)
+    assert rel.max() <= 1e-5, rel.max()
+    assert (b == want).mean() > 0.99
+
+
+def test_tile_path_equals_generic_path():
+    """The tile sweep and the generic sweep are two schedules of the same arithmetic."""
+    w = workloads.make("merger_1e6", n_gas=150_000)
+    g1 = tc.HotPath.from_workload(w)
+    os.environ["TOYGPU_NO_TILES"] = "1"
+    try:
+        g2 = tc.HotPath.from_workload(w)
+    finally:
+        del os.environ["TOYGPU_NO_TILES"]
+    for g in (g1, g2):
+        g.upload(w.pos)
+    tiled = 0
+    for it in range(4):
+        for g in (g1, g2):
+            g.find_sph_quantities()
+        a, b = g1.download(), g2.download()
+        for k in ("id", "pos", "hsml", "rho", "varhsml"):
+            assert np.array_equal(a[k], b[k]), (it, k)
+        if it > 0:
+            tiled += w.n_gas - g1.stats()["handed_back"]
+    assert tiled > 2 * w.n_gas          # the fast path really ran
+
+
+def test_rank_slices_equal_single_rank():
+    """Two contexts on one GPU play ranks 0 and 1 of 2 (host copies stand in for the
+    all-gather): positions, Hsml and densities equal the one-rank run bit for bit."""
+    w = workloads.make("merger_1e6", n_gas=40_003)          # ragged on purpose
+    one = tc.HotPath.from_workload(w, flags=tc.WVT_SEQUENTIAL)
+    parts = [tc.HotPath.from_workload(w, flags=tc.WVT_SEQUENTIAL, rank=r, nranks=2) for r in range(2)]
+    state_pos, state_h = w.pos, None
+    one.upload(w.pos)
+    for it in range(3):
+        one.wvt_iteration(0.0085)
+        ref = one.download()
+        merged = {}
+        for r, g in enumerate(parts):
+            g.upload(state_pos, state_h)
+            g.wvt_iteration(0.0085)
+            o = g.download()
+            lo, hi, _ = rank_slice(w.n_gas, r, 2)
+            for k in ("pos", "hsml", "rho", "varhsml", "id"):
+                merged.setdefault(k, np.empty_like(o[k]))[lo:hi] = o[k][lo:hi]
+        # ids of the slice runs are relative to the re-uploaded order; map back
+        if it == 0:
+            ids = merged["id"]
+        else:
+            ids = prev_ids[merged["id"]]
+        for k in ("pos", "hsml", "rho", "varhsml"):
+            assert np.array_equal(merged[k], ref[k]), (it, k)
+        assert np.array_equal(ids, ref["id"])
+        prev_ids, state_pos, state_h = ids, merged["pos"], merged["hsml"]
+
+
+def test_records_travel_with_the_particle():
+    """tg_upload / tg_download on the driver's AoS records (globals.h:161-180)."""
+    w = workloads.make("merger_1e6", n_gas=20_000)
+    n = w.n_gas
+    P = np.zeros(n, dtype=np.dtype([("Pos", "3f4"), ("Vel", "3f4"), ("ID", "i4"), ("Type", "i4"),
+                                     ("Key", "2u8"), ("Tree_Parent", "i4"), ("pad", "3i4")]))
+    S = np.zeros(n, dtype=np.dtype([("U", "f4"), ("Rho", "f4"), ("Hsml", "f4"), ("VarHsmlFac", "f4"),
+                                     ("Bfld", "3f4"), ("Apot", "3f4"), ("ID", "f4"),
+                                     ("Rho_Model", "f4"), ("Rs", "3f4")]))
+    assert P.itemsize == 64 and S.itemsize == 60
+    P["Pos"], P["ID"], P["Vel"][:, 0] = w.pos, np.arange(n) * 7 + 3, np.arange(n)
+    S["U"], S["ID"] = np.arange(n) * 0.5, np.arange(n) * 7 + 3
+    g = tc.HotPath.from_workload(w)
+    g.upload_records(P, S)
+    g.find_sph_quantities()
+    o = g.download()
+    g.download_records(P, S)
+    assert np.array_equal(P["ID"], o["id"] * 7 + 3)             # whole records were permuted
+    assert np.array_equal(P["Vel"][:, 0], o["id"].astype(np.float32))
+    assert np.array_equal(S["U"], o["id"] * np.float32(0.5)) and np.array_equal(S["ID"], P["ID"])
+    assert np.array_equal(P["Pos"], o["pos"]) and np.array_equal(P["Pos"], w.pos[o["id"]])
+    assert np.array_equal(S["Hsml"], o["hsml"]) and np.array_equal(S["Rho"], o["rho"])
+    assert np.array_equal(S["VarHsmlFac"], o["varhsml"]) and np.array_equal(S["Rho_Model"], o["rho_model"])
+    key = (P["Key"][:, 1].astype(object) << 64) | P["Key"][:, 0].astype(object)
+    assert all(key[k] < key[k + 1] for k in range(n - 1))       # Peano order of the last sort

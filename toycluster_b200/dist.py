@@ -1,0 +1,44 @@
+"""Host-side plumbing for one-process-per-GPU runs.
+
+The path shards by TARGET particle: every rank holds all positions, sorts and indexes them
+redundantly (bit-identical on every rank), sweeps the Peano-order slice
+``[rank*chunk, min(n, (rank+1)*chunk))`` and then the moved ``(x, y, z, Hsml)`` slices are
+re-assembled with ONE all-gather per step; the error statistics of wvt_relax.c:73-87 need one
+all-reduce of two scalars.  Works on NCCL (device tensors wrapping the library's buffers) and
+on gloo (CPU tensors; used by the world-size-2 tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def rank_slice(n: int, rank: int, nranks: int):
+    """Mirror of tg_create's partition: equal chunks of whole 32-target tiles."""
+    chunk = ((n + nranks - 1) // nranks + 31) // 32 * 32
+    lo = min(n, rank * chunk)
+    hi = min(n, lo + chunk)
+    return lo, hi, chunk
+
+
+def allgather_slices(full: torch.Tensor, rank: int, chunk: int, width: int) -> None:
+    """In-place all-gather: ``full`` holds nranks*chunk records of ``width`` elements and this
+    rank's records are already in place."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    mine = full[rank * chunk * width:(rank + 1) * chunk * width]
+    if full.is_cuda:
+        dist.all_gather_into_tensor(full, mine)        # NCCL: in place
+    else:
+        dist.all_gather_into_tensor(full, mine.clone())
+
+
+def reduce_errors(err_sum: float, err_max: float, count: int, device="cpu"):
+    """Global (errMax, errMean) from per-rank sums (wvt_relax.c:73-87)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return err_max, (err_sum / count if count else 0.0)
+    s = torch.tensor([err_sum, float(count)], dtype=torch.float64, device=device)
+    m = torch.tensor([err_max], dtype=torch.float64, device=device)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    return m.item(), s[0].item() / s[1].item()
