@@ -20,6 +20,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_ref", "libtoyref.so")
+# Same harness API, but the three operators are toycluster_b200/host/gpu_shim.c + libtoygpu.so
+SHIM = os.path.join(HERE, "_ref", "libtoyshim.so")
 
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -44,29 +46,35 @@ def build() -> bool:
 class Ref:
     NGBMAX = 2360
 
-    def __init__(self, n_gas, boxsize, mpart, mtotal, halo_table, nthreads=0):
-        if not available():
-            raise RuntimeError("oracle/_ref/libtoyref.so missing: run `make -C oracle ref`")
+    def __init__(self, n_gas, boxsize, mpart, mtotal, halo_table, nthreads=0, shim=False):
+        src = SHIM if shim else LIB
+        if not os.path.exists(src):
+            raise RuntimeError(f"{src} missing: run `make -C oracle ref shim`")
+        if shim:   # resolve the shim's DT_NEEDED libtoygpu.so by soname
+            gpu = os.path.join(os.path.dirname(HERE), "toycluster_b200", "libtoygpu.so")
+            self._gpu = C.CDLL(gpu, mode=C.RTLD_GLOBAL)
         self._tmp = tempfile.NamedTemporaryFile(suffix=".so", delete=False)
         self._tmp.close()
-        shutil.copyfile(LIB, self._tmp.name)
+        shutil.copyfile(src, self._tmp.name)
         lib = self.lib = C.CDLL(self._tmp.name)
         os.unlink(self._tmp.name)
         self.n = int(n_gas)
         halo_table = np.ascontiguousarray(halo_table, dtype=np.float64).reshape(-1, 9)
         lib.ref_setup.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                   np.ctypeslib.ndpointer(np.float64), C.c_int]
-        lib.ref_guess_hsml.restype = C.c_float
-        lib.ref_guess_hsml.argtypes = [C.c_int]
+        if not shim:
+            lib.ref_guess_hsml.restype = C.c_float
+            lib.ref_guess_hsml.argtypes = [C.c_int]
+            lib.ref_find_ngb_tree.argtypes = [C.c_int, C.c_float, _i32p]
+            lib.ref_find_ngb_simple.argtypes = [C.c_int, C.c_float, _i32p]
+            lib.ref_peano_key.argtypes = [C.c_double, C.c_double, C.c_double,
+                                          C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong),
+                                          C.c_int]
         lib.ref_global_density_model.restype = C.c_float
-        lib.ref_find_ngb_tree.argtypes = [C.c_int, C.c_float, _i32p]
-        lib.ref_find_ngb_simple.argtypes = [C.c_int, C.c_float, _i32p]
         lib.ref_log.restype = C.c_char_p
         lib.ref_time_density.restype = C.c_double
         lib.ref_wvt_scratch.restype = C.POINTER(C.c_float)
         lib.ref_regularise.argtypes = [C.c_int, C.c_void_p, C.c_int]
-        lib.ref_peano_key.argtypes = [C.c_double, C.c_double, C.c_double,
-                                      C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
         rc = lib.ref_setup(self.n, boxsize, mpart, mtotal, len(halo_table), halo_table,
                            int(nthreads))
         if rc != 0:

@@ -129,6 +129,7 @@ void *refhook_malloc(const char *func, const char *file, const int line, size_t 
     return ptr;
 }
 
+#ifndef SHIM_BUILD
 /* Called by wvt_relax.c:67 in place of Find_sph_quantities(). At entry the scratch
  * arrays hsml[]/delta[][] still hold the previous iteration's values in the particle
  * order of the previous sort, and P.Pos has been moved (wvt_relax.c:193-213). */
@@ -146,6 +147,7 @@ void refhook_find_sph(void)
     Find_sph_quantities();
     Time_density += omp_get_wtime() - t0;
 }
+#endif
 
 /* ------------------------------------------------------------------ API */
 
@@ -254,6 +256,11 @@ void ref_read(float *pos, int *id, float *hsml, float *rho, float *varhsml,
     }
 }
 
+#ifdef SHIM_BUILD
+/* libtoyshim.so: the same harness, but the three operators come from
+ * toycluster_b200/host/gpu_shim.c + libtoygpu.so instead of sph.c / wvt_relax.c. */
+void toyshim_set_max_iters(int n);
+#else
 void ref_peano_key(double x, double y, double z, unsigned long long *hi,
                    unsigned long long *lo, int reversed)
 {
@@ -261,12 +268,15 @@ void ref_peano_key(double x, double y, double z, unsigned long long *hi,
     *hi = (unsigned long long)(k >> 64);
     *lo = (unsigned long long)k;
 }
+#endif
 
+#ifndef SHIM_BUILD
 void ref_sort(void) { Sort_Particles_By_Peano_Key(); }
 void ref_build_tree(void) { Build_Tree(); }
 int ref_find_ngb_tree(int ipart, float hsml, int *list) { return Find_ngb_tree(ipart, hsml, list); }
 int ref_find_ngb_simple(int ipart, float hsml, int *list) { return Find_ngb_simple(ipart, hsml, list); }
 float ref_guess_hsml(int ipart) { return Guess_hsml(ipart, DESNNGB); }
+#endif
 float ref_global_density_model(int ipart) { return Global_density_model(ipart); }
 void ref_find_sph_quantities(void) { Find_sph_quantities(); }
 void ref_bfld_from_rotA(void) { Bfld_from_rotA_SPH(); }
@@ -290,10 +300,16 @@ int ref_regularise(int max_iters, int (*cb)(int), int echo)
     Log_echo = echo;
     Time_density = 0;
 
+#ifdef SHIM_BUILD
+    toyshim_set_max_iters(max_iters);
+    Regularise_sph_particles();
+    return max_iters;
+#else
     if (setjmp(Stop_env) == 0)
         Regularise_sph_particles();
     else
         Wvt_leaked = 1;
+#endif
 
     Iter_cb = NULL;
     return Iter_seen;

@@ -69,8 +69,8 @@ static __device__ __forceinline__ double block_max(double v, double *sm)
 __global__ void __launch_bounds__(RED_THREADS)
 k_reorder_model(int n, const int *__restrict__ idx, const float4 *__restrict__ posh_in,
                 const int *__restrict__ id_in, const uint64_t *__restrict__ key_lo_in,
-                const float *__restrict__ apot_in,
-                float4 *__restrict__ pw, float *__restrict__ hsml, int *__restrict__ id_out,
+                const float *__restrict__ apot_in, const float *__restrict__ rmstate_in,
+                float *__restrict__ rmstate_out, float4 *__restrict__ pw, float *__restrict__ hsml, int *__restrict__ id_out,
                 float *__restrict__ rho_model, uint64_t *__restrict__ key_lo_out,
                 float *__restrict__ apot_out,
                 const Halo *__restrict__ halos, int nhalos, double mpart, double boxhalf,
@@ -90,6 +90,7 @@ k_reorder_model(int n, const int *__restrict__ idx, const float4 *__restrict__ p
         id_out[k] = id_in[src];
         rho_model[k] = rm;
         key_lo_out[k] = key_lo_in[src];
+        rmstate_out[k] = rmstate_in[src];      // SphP.Rho_Model travels with the record
         if (apot_in) {
             apot_out[3 * k] = apot_in[3 * src];
             apot_out[3 * k + 1] = apot_in[3 * src + 1];

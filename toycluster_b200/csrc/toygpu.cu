@@ -60,6 +60,7 @@ struct tg_ctx {
     // sorted
     float4 *pw = nullptr;
     float *hsml_in = nullptr, *rho_model = nullptr;
+    float *rm_state = nullptr, *rm_state_s = nullptr;   // SphP.Rho_Model as the driver sees it (current order)
     int *id_s = nullptr;
     uint64_t *key_lo_s = nullptr;
     float *apot_s = nullptr;
@@ -143,7 +144,7 @@ extern "C" int tg_destroy(tg_ctx *c)
     if (!c) return TG_OK;
     cudaSetDevice(c->cfg.device);
     void *ptrs[] = {c->posh, c->id, c->apot, c->stage, c->key_hi, c->key_lo, c->key_tmp, c->idx, c->idx_tmp,
-                    c->hist, c->pw, c->hsml_in, c->rho_model, c->id_s, c->key_lo_s, c->apot_s,
+                    c->hist, c->pw, c->hsml_in, c->rho_model, c->rm_state, c->rm_state_s, c->id_s, c->key_lo_s, c->apot_s,
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->sub_mem, c->cpl,
                     c->ev_level, c->ev_count, c->ev_start, c->guess, c->halos, c->partial, c->scal,
                     c->flags, c->counters, c->gscratch, c->tile_ng, c->tile_groups, c->worklist};
@@ -221,6 +222,9 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     CUC(dmalloc(&c->pw, n));
     CUC(dmalloc(&c->hsml_in, n));
     CUC(dmalloc(&c->rho_model, n));
+    CUC(dmalloc(&c->rm_state, n));
+    CUC(dmalloc(&c->rm_state_s, n));
+    CUC(cudaMemsetAsync(c->rm_state, 0, sizeof(float) * n, c->stream));
     CUC(dmalloc(&c->id_s, n));
     CUC(dmalloc(&c->key_lo_s, n));
     CUC(dmalloc(&c->hsml_out, n));
@@ -359,6 +363,7 @@ static int upload_common(tg_ctx *c, const float *pos, const float *hsml)
     c->any_cold = cold != 0;
     c->index_valid = false;
     c->have_apot = false;
+    CU(cudaMemsetAsync(c->rm_state, 0, sizeof(float) * n, c->stream));
     return TG_OK;
 }
 
@@ -372,18 +377,23 @@ extern "C" int tg_upload(tg_ctx *c, const void *P, size_t p_stride, const void *
 {
     if (!c || !P || !SphP || p_stride < 12 || s_stride < 12)
         return fail(c, TG_EINVAL, "tg_upload: bad arguments");
-    std::vector<float> pos((size_t)3 * c->n), hsml(c->n);
+    std::vector<float> pos((size_t)3 * c->n), hsml(c->n), rhom(c->n, 0.f);
     std::vector<float> apot((size_t)3 * c->n);
-    const bool with_apot = s_stride >= 40;
+    const bool with_apot = s_stride >= 40, with_rhom = s_stride >= 48;
     for (int i = 0; i < c->n; i++) {
         const float *pp = (const float *)((const char *)P + i * p_stride);             // Pos @ +0
         const float *sph = (const float *)((const char *)SphP + i * s_stride);
         pos[3 * (size_t)i] = pp[0]; pos[3 * (size_t)i + 1] = pp[1]; pos[3 * (size_t)i + 2] = pp[2];
         hsml[i] = sph[2];                                                               // Hsml @ +8
         if (with_apot) for (int k = 0; k < 3; k++) apot[3 * (size_t)i + k] = sph[7 + k];   // Apot @ +28
+        if (with_rhom) rhom[i] = sph[11];                                               // Rho_Model @ +44
     }
     int rc = upload_common(c, pos.data(), hsml.data());
     if (rc == TG_OK && with_apot) rc = tg_set_apot(c, apot.data());
+    if (rc == TG_OK && with_rhom) {
+        CU(cudaMemcpyAsync(c->rm_state, rhom.data(), sizeof(float) * c->n, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
     return rc;
 }
 
@@ -451,7 +461,8 @@ static int prepare_index(tg_ctx *c)
     if (rc) return rc;
 
     k_reorder_model<<<c->npartial, RED_THREADS, 0, c->stream>>>(
-        n, c->idx_s, c->posh, c->id, c->key_lo, c->have_apot ? c->apot : nullptr, c->pw, c->hsml_in,
+        n, c->idx_s, c->posh, c->id, c->key_lo, c->have_apot ? c->apot : nullptr, c->rm_state,
+        c->rm_state_s, c->pw, c->hsml_in,
         c->id_s, c->rho_model, c->key_lo_s, c->apot_s, c->halos, c->nhalos, c->box.mpart,
         c->box.boxhalf_d, c->partial);
     LAUNCH_CHECK();
@@ -488,6 +499,7 @@ static int prepare_index(tg_ctx *c)
 
     // the sorted order is now the current order
     std::swap(c->id, c->id_s);
+    std::swap(c->rm_state, c->rm_state_s);
     if (c->have_apot) std::swap(c->apot, c->apot_s);
     c->index_valid = true;
     return TG_OK;
@@ -617,6 +629,8 @@ static int displacement_pass(tg_ctx *c, double step)
 
 static int move_pass(tg_ctx *c)
 {
+    // wvt_relax.c:113: SphP.Rho_Model is (only) written by the model-hsml pass of an iteration
+    CU(cudaMemcpyAsync(c->rm_state, c->rho_model, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, c->stream));
     if (c->hi > c->lo)
         k_move<<<cdiv(c->hi - c->lo, 256), 256, 0, c->stream>>>(c->lo, c->hi, c->n, c->pw, c->hsml_out, c->delta,
                                                                c->box.box_d, 1.0, c->posh);
@@ -787,7 +801,7 @@ extern "C" int tg_download_soa(tg_ctx *c, float *pos, int32_t *perm, float *hsml
     if (perm) CU(cudaMemcpyAsync(perm, c->id, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
     if (rho) CU(cudaMemcpyAsync(rho, c->rho, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     if (varhsml) CU(cudaMemcpyAsync(varhsml, c->varh, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-    if (rho_model) CU(cudaMemcpyAsync(rho_model, c->rho_model, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    if (rho_model) CU(cudaMemcpyAsync(rho_model, c->rm_state, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     if (bfld) CU(cudaMemcpyAsync(bfld, c->bfld, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return TG_OK;

@@ -1,0 +1,150 @@
+/*
+ * gpu_shim.c -- the reference's three hot-path entry points on top of libtoygpu.so.
+ *
+ * Compiled WITH the reference's own headers (globals.h, proto.h) and linked into the
+ * unmodified driver in place of tree.o sph.o wvt_relax.o peano.o (keep sort.o: positions.c:409
+ * uses Qsort_Index).  It defines exactly the symbols main.c:52-56 and magnetic_field.c:21
+ * call, with the reference's conventions:
+ *
+ *   void Regularise_sph_particles();   wvt_relax.c:25
+ *   void Find_sph_quantities();        sph.c:13
+ *   void Bfld_from_rotA_SPH();         sph.c:216
+ *   float Global_density_model(int);   wvt_relax.c:227 (proto.h:46)
+ *
+ *   - state lives in the driver's globals P, SphP, Param, Halo[]; only the gas range
+ *     [0, Param.Npart[0]) is touched and whole records are permuted into Peano order;
+ *   - no return codes: a library failure is reported like Assert() does (aux.c:57-83) --
+ *     message on stderr, exit(EXIT_FAILURE);
+ *   - the '#NN: Err max=...' line and the banners of wvt_relax.c:31-34,91-92,222 are
+ *     printed from the library's per-iteration callback.
+ * The device context is created on first use and kept for the process lifetime, like the
+ * reference's static Keys/Idx/Tree buffers (peano.c:53-61, tree.c:343-346).
+ */
+#include "globals.h"
+#include "toygpu.h"
+
+static tg_ctx *Ctx = NULL;
+static int Shim_max_iters = 1 << 30;
+static unsigned Shim_flags = 0;
+
+void toyshim_set_max_iters(int n) { Shim_max_iters = n; }      /* tests only */
+void toyshim_set_flags(unsigned f) { Shim_flags = f; }          /* before first use */
+
+static void check(int rc, const char *what)
+{
+    Assert(rc == TG_OK, "libtoygpu: %s failed (%d): %s", what, rc, tg_last_error(Ctx));
+}
+
+static void ensure_context(void)
+{
+    if (Ctx != NULL)
+        return;
+
+    tg_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.device = getenv("TOYGPU_DEVICE") ? atoi(getenv("TOYGPU_DEVICE")) : 0;
+    cfg.n_gas = Param.Npart[0];
+    cfg.boxsize = Param.Boxsize;
+    cfg.mpart_gas = Param.Mpart[0];
+    cfg.mtotal = Param.Mtotal;
+    cfg.flags = Shim_flags;
+    cfg.rank = 0;
+    cfg.nranks = 1;
+
+    int rc = tg_create(&Ctx, &cfg);
+    Assert(rc == TG_OK, "libtoygpu: tg_create failed (%d): %s", rc, tg_last_error(NULL));
+
+    tg_halo *rows = Malloc(Param.Nhalos * sizeof *rows);
+    for (int i = 0; i < Param.Nhalos; i++) {
+        for (int k = 0; k < 3; k++)
+            rows[i].dcom[k] = Halo[i].D_CoM[k];
+        rows[i].rho0 = Halo[i].Rho0;
+        rows[i].beta = Halo[i].Beta;
+        rows[i].rcore = Halo[i].Rcore;
+        rows[i].rcut = Halo[i].Rcut;
+        rows[i].cuspy = Halo[i].Have_Cuspy;
+        rows[i].mass_gas = Halo[i].Mass[0];
+    }
+    check(tg_set_halos(Ctx, Param.Nhalos, rows), "tg_set_halos");
+    Free(rows);
+}
+
+void Find_sph_quantities()
+{
+    ensure_context();
+    check(tg_upload(Ctx, P, sizeof *P, SphP, sizeof *SphP), "tg_upload");
+    check(tg_find_sph_quantities(Ctx), "tg_find_sph_quantities");
+    check(tg_download(Ctx, P, sizeof *P, SphP, sizeof *SphP), "tg_download");
+}
+
+static int print_iteration(int it, double err_max, double err_mean, double err_diff,
+                           double step, void *user)
+{
+    (void)user;
+    printf("   #%02d: Err max=%3g mean=%03g diff=%03g"
+           " step=%g\n", it, err_max, err_mean, err_diff, step);
+    return 0;
+}
+
+void Regularise_sph_particles()
+{
+    printf("Starting iterative SPH regularisation \n"
+           "   max %d iterations, tree update every %d iterations\n"
+           "   stop at  errmax < %g%%   \n\n", TG_NUMITER, 1, 0.01 * 100);
+    fflush(stdout);
+
+    ensure_context();
+    int done = 0;
+    check(tg_upload(Ctx, P, sizeof *P, SphP, sizeof *SphP), "tg_upload");
+    check(tg_regularise(Ctx, Shim_max_iters, &print_iteration, NULL, &done), "tg_regularise");
+    check(tg_download(Ctx, P, sizeof *P, SphP, sizeof *SphP), "tg_download");
+
+    printf("\ndone\n\n");
+    fflush(stdout);
+}
+
+void Bfld_from_rotA_SPH()
+{
+    printf("Constructing B from rot(A)");
+    fflush(stdout);
+
+    ensure_context();
+    const int n = Param.Npart[0];
+    float *buf = Malloc((size_t)3 * n * sizeof *buf);
+
+    /* Apot was set by the driver on the records in their current order
+     * (magnetic_field.c:33-69), which is the library's current order too */
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++)
+            buf[3 * (size_t)i + k] = SphP[i].Apot[k];
+    check(tg_set_apot(Ctx, buf), "tg_set_apot");
+    check(tg_bfld_from_rotA(Ctx), "tg_bfld_from_rotA");
+    check(tg_download_soa(Ctx, NULL, NULL, NULL, NULL, NULL, NULL, buf), "tg_download_soa");
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++)
+            SphP[i].Bfld[k] = buf[3 * (size_t)i + k];
+    Free(buf);
+
+    printf(" done \n\n");
+    fflush(stdout);
+}
+
+/* wvt_relax.c:227-256; host-side, for callers outside the path (proto.h:46). */
+float Global_density_model(const int ipart)
+{
+    const double boxhalf = Param.Boxsize * 0.5;
+    const double x = P[ipart].Pos[0], y = P[ipart].Pos[1], z = P[ipart].Pos[2];
+    double rho = 0;
+
+    for (int i = 0; i < Param.Nhalos; i++) {
+        if (Halo[i].Mass[0] == 0)
+            continue;
+        const double dx = x - Halo[i].D_CoM[0] - boxhalf;
+        const double dy = y - Halo[i].D_CoM[1] - boxhalf;
+        const double dz = z - Halo[i].D_CoM[2] - boxhalf;
+        const double rho_i = Gas_density_profile(sqrt(dx * dx + dy * dy + dz * dz), Halo[i].Rho0,
+                                Halo[i].Beta, Halo[i].Rcore, Halo[i].Rcut, Halo[i].Have_Cuspy);
+        rho = fmax(rho_i, rho);
+    }
+    return rho;
+}
