@@ -212,10 +212,10 @@ def main():
     posh_full = torch.as_tensor(_Dev(ex.pos_hsml_dev, npad * 16), device="cuda").view(torch.float32)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if n * 16 <= L2_BYTES else None
 
+    from toycluster_b200.dist import allgather_slices
+
     def exchange():
-        if world > 1:
-            mine = posh_full[rank * chunk * 4:(rank + 1) * chunk * 4]
-            dist.all_gather_into_tensor(posh_full, mine)
+        allgather_slices(posh_full, rank, chunk, 4)     # one in-place NCCL all-gather per step
 
     def one_step(step):
         if flush is not None:
