@@ -218,7 +218,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     CUC(dmalloc(&c->idx, n));
     CUC(dmalloc(&c->idx_tmp, n));
     c->ntiles = cdiv(n, RS_TILE);
-    CUC(dmalloc(&c->hist, (size_t)RS_BINS * c->ntiles));
+    CUC(dmalloc(&c->hist, (size_t)RS_BINS * c->ntiles + RS_BINS));   // + digit totals
     CUC(dmalloc(&c->pw, n));
     CUC(dmalloc(&c->hsml_in, n));
     CUC(dmalloc(&c->rho_model, n));
@@ -437,10 +437,11 @@ static int sort_keys(tg_ctx *c)
     for (int shift = 0; shift < 64; shift += RS_BITS) {
         k_radix_hist<<<c->ntiles, RS_THREADS, 0, c->stream>>>(n, kin, shift, c->ntiles, c->hist);
         LAUNCH_CHECK();
-        k_radix_scan<<<1, 1024, 0, c->stream>>>((size_t)RS_BINS * c->ntiles, c->hist);
+        unsigned *bin_total = c->hist + (size_t)RS_BINS * c->ntiles;
+        k_radix_scan<<<RS_BINS, 1024, 0, c->stream>>>(c->ntiles, c->hist, bin_total);
         LAUNCH_CHECK();
         k_radix_scatter<<<c->ntiles, RS_THREADS, 0, c->stream>>>(n, kin, iin, kout, iout, shift,
-                                                                c->ntiles, c->hist);
+                                                                c->ntiles, c->hist, bin_total);
         LAUNCH_CHECK();
         std::swap(kin, kout);
         std::swap(iin, iout);
