@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--sequential", action="store_true", help="TG_WVT_SEQUENTIAL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--full-relaxation", action="store_true",
+                    help="also time Regularise_sph_particles from the cold start to its own termination")
     return ap.parse_args()
 
 
@@ -228,6 +230,7 @@ def main():
     pos_host = torch.from_numpy(w.pos).pin_memory()
     hsml_host = torch.zeros(n, dtype=torch.float32).pin_memory()
     pos_np, hsml_np = pos_host.numpy(), hsml_host.numpy()
+    pos_np0 = w.pos.copy()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -289,6 +292,21 @@ def main():
                "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
                "ms_per_step": dt.item() * 1e3 / args.steps}
 
+    full = None
+    if args.full_relaxation:
+        from toycluster_b200.dist import regularise as regularise_ranks
+        g.upload(pos_np0)
+        sync_all()
+        t0 = time.perf_counter()
+        if world == 1:
+            iters, rows = g.regularise_sph_particles()
+        else:
+            rows = regularise_ranks(g, exchange, mtotal=w.mtotal, device="cuda")
+            iters = len(rows)
+        sync_all()
+        full = {"iterations": iters, "seconds": time.perf_counter() - t0,
+                "final_err_mean": rows[-1]["mean"], "final_step": rows[-1]["step"]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -323,6 +341,8 @@ def main():
             "gpu_launches": int(acc["kernels"]), "clocks": clocks, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e
+    if full:
+        line["full_relaxation"] = full
     if not args.no_cpu_baseline and world == 1:
         res = run_reference(args.workload, n, 2, 1)
         if res:

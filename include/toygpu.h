@@ -119,6 +119,14 @@ int tg_bfld_from_rotA(tg_ctx *ctx);                            /* == sph.c:216  
  * and the per-iteration parity tests).  Runs sort + index + density + error + model hsml +
  * displacement + move; err_max/err_mean as at wvt_relax.c:73-87. */
 int tg_wvt_iteration(tg_ctx *ctx, double step, double *err_max, double *err_mean);
+/* The same pass in two halves, for hosts that own the control flow of wvt_relax.c:89-104
+ * (tg_regularise itself, and multi-rank hosts that must all-reduce the error statistics):
+ * begin = sort + index + density (+ displacement with step_guess unless TG_WVT_SEQUENTIAL)
+ * and the error sum / max / count of this rank's slice; finish = displacement with the final
+ * step (a rescale when it was already computed) + move, or with step_final <= 0 the
+ * reference's `break`: positions stay, the new Hsml is kept. */
+int tg_wvt_begin(tg_ctx *ctx, double step_guess, double *err_sum, double *err_max, int *count);
+int tg_wvt_finish(tg_ctx *ctx, double step_final);
 /* Scratch of the last iteration (wvt_relax.c:36-44), in that iteration's Peano order. */
 int tg_wvt_scratch(tg_ctx *ctx, float *hsml_wvt, float *delta /* [n][3] */);
 

@@ -201,3 +201,53 @@ def test_regularise_loop_matches_log(wl2):
             assert _same_as_printed(rows[it][k], log[it][k]), (it, k, rows[it][k], log[it][k])
     o = g.download()
     assert np.array_equal(o["pos"], after[-1]["pos"])
+
+
+def test_full_relaxation_sequential_and_statistical(wl2):
+    """The whole Regularise_sph_particles loop to its own termination (wvt_relax.c:94-98).
+    Sequential mode: every printed line and the final state are the reference's.  Default
+    mode (FP64 tree sum, fused sweep): iterated relaxation is chaotic at the float-ulp level,
+    so the comparison is statistical -- same iteration count, same error history to 1e-3,
+    same density-error distribution and radial profile."""
+    w = wl2
+    r = _ref(w)
+    r.load(w.pos)
+    r.regularise()
+    log = ref.parse_log(r.log())
+    r.find_sph_quantities()
+    want = r.read()
+    assert 12 <= len(log) <= 65
+
+    g = tc.HotPath.from_workload(w, flags=tc.WVT_SEQUENTIAL)
+    g.upload(w.pos)
+    done, rows = g.regularise_sph_particles()
+    g.find_sph_quantities()
+    got = g.download()
+    assert done == len(log)
+    for a, b in zip(rows, log):
+        for k in ("max", "mean", "diff", "step"):
+            assert _same_as_printed(a[k], b[k]), (a["it"], k, a[k], b[k])
+    for k in ("id", "pos", "hsml", "rho", "varhsml"):
+        assert np.array_equal(got[k], want[k]), k
+
+    g = tc.HotPath.from_workload(w)
+    g.upload(w.pos)
+    done, rows = g.regularise_sph_particles()
+    g.find_sph_quantities()
+    got = g.download()
+    assert abs(done - len(log)) <= 1
+    for a, b in zip(rows, log):
+        assert abs(a["mean"] - b["mean"]) <= 1e-3 * b["mean"], (a["it"], a["mean"], b["mean"])
+        assert _same_as_printed(a["step"], b["step"])
+    # density-error distribution |rho - rho_model| / rho_model
+    def err(s):
+        rm = s["rho_model"].astype(np.float64)
+        return np.abs(s["rho"] - rm) / rm
+    qs = [0.1, 0.25, 0.5, 0.75, 0.9, 0.99]
+    assert np.allclose(np.quantile(err(got), qs), np.quantile(err(want), qs), rtol=2e-2)
+    # radial number profile around the main halo
+    centre = np.array(w.halos[0].dcom) + w.boxsize / 2
+    bins = np.geomspace(30, 6000, 16)
+    ha, _ = np.histogram(np.linalg.norm(got["pos"] - centre, axis=1), bins)
+    hb, _ = np.histogram(np.linalg.norm(want["pos"] - centre, axis=1), bins)
+    assert np.all(np.abs(ha - hb) <= 3 + 4 * np.sqrt(np.maximum(hb, 1)) * 0.2), (ha, hb)

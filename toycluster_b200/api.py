@@ -68,7 +68,7 @@ _LOG_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_
 EXPORTS = [
     "tg_create", "tg_destroy", "tg_last_error", "tg_set_halos", "tg_upload", "tg_upload_soa",
     "tg_set_apot", "tg_download", "tg_download_soa", "tg_find_sph_quantities", "tg_regularise",
-    "tg_bfld_from_rotA", "tg_wvt_iteration", "tg_wvt_scratch", "tg_get_stats", "tg_peano_keys",
+    "tg_bfld_from_rotA", "tg_wvt_iteration", "tg_wvt_begin", "tg_wvt_finish", "tg_wvt_scratch", "tg_get_stats", "tg_peano_keys",
     "tg_sort", "tg_find_ngb", "tg_guess_hsml", "tg_get_exchange",
 ]
 
@@ -111,6 +111,9 @@ def load():
     lib.tg_bfld_from_rotA.argtypes = [C.c_void_p]
     lib.tg_wvt_iteration.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double),
                                      C.POINTER(C.c_double)]
+    lib.tg_wvt_begin.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    lib.tg_wvt_finish.argtypes = [C.c_void_p, C.c_double]
     lib.tg_wvt_scratch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tg_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.tg_peano_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -233,6 +236,16 @@ class HotPath:
         self._check(self.lib.tg_wvt_iteration(self._ctx, float(step), C.byref(emax),
                                               C.byref(emean)))
         return emax.value, emean.value
+
+    def wvt_begin(self, step_guess):
+        """-> (err_sum, err_max, count) of this rank's slice (wvt_relax.c:73-87)."""
+        s, m, n = C.c_double(), C.c_double(), C.c_int()
+        self._check(self.lib.tg_wvt_begin(self._ctx, float(step_guess), C.byref(s), C.byref(m),
+                                          C.byref(n)))
+        return s.value, m.value, n.value
+
+    def wvt_finish(self, step_final):
+        self._check(self.lib.tg_wvt_finish(self._ctx, float(step_final)))
 
     def wvt_scratch(self):
         h = np.empty(self.n, np.float32)

@@ -149,7 +149,7 @@ k_final_err(int count, const double *__restrict__ partial, double *__restrict__ 
 // (with the freshly solved Hsml) becomes the next iteration's unsorted input.
 // `scale` rescales a displacement computed with a stale step (fused sweep); 1 otherwise.
 __global__ void k_move(int lo, int hi, int n, const float4 *__restrict__ pw,
-                       const float *__restrict__ hsml, const float *__restrict__ delta, double box,
+                       const float *__restrict__ hsml, float *__restrict__ delta, double box,
                        double scale, float4 *__restrict__ posh_out)
 {
     const int k = lo + blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,7 +159,10 @@ __global__ void k_move(int lo, int hi, int n, const float4 *__restrict__ pw,
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         float d = delta[(size_t)a * n + k];
-        if (scale != 1.0) d = (float)((double)d * scale);
+        if (scale != 1.0) {      // the sweep ran with the step as it stood before wvt_relax.c:100
+            d = (float)((double)d * scale);
+            delta[(size_t)a * n + k] = d;
+        }
         float x = __fadd_rn(c[a], (float)((double)d * box));
         for (int guard = 0; guard < 64 && (double)x < 0; guard++) x = (float)((double)x + box);
         for (int guard = 0; guard < 64 && (double)x > box; guard++) x = (float)((double)x - box);

@@ -39,6 +39,7 @@ struct tg_ctx {
     int n = 0, lo = 0, hi = 0, chunk = 0;
     Box box{};
     double bias_const = 0;
+    double step_begin = 0;          // step the last tg_wvt_begin swept with
 
     // state (current order)
     float4 *posh = nullptr;
@@ -628,13 +629,13 @@ static int displacement_pass(tg_ctx *c, double step)
     return launch_sweep<MODE_WVT>(c, a);
 }
 
-static int move_pass(tg_ctx *c)
+static int move_pass(tg_ctx *c, double scale)
 {
     // wvt_relax.c:113: SphP.Rho_Model is (only) written by the model-hsml pass of an iteration
     CU(cudaMemcpyAsync(c->rm_state, c->rho_model, sizeof(float) * c->n, cudaMemcpyDeviceToDevice, c->stream));
     if (c->hi > c->lo)
         k_move<<<cdiv(c->hi - c->lo, 256), 256, 0, c->stream>>>(c->lo, c->hi, c->n, c->pw, c->hsml_out, c->delta,
-                                                               c->box.box_d, 1.0, c->posh);
+                                                               c->box.box_d, scale, c->posh);
     LAUNCH_CHECK();
     return TG_OK;
 }
@@ -681,38 +682,77 @@ extern "C" int tg_find_sph_quantities(tg_ctx *c)
     return finish_stats(c, true);
 }
 
-extern "C" int tg_wvt_iteration(tg_ctx *c, double step, double *err_max, double *err_mean)
+// First half of one pass of wvt_relax.c:66-214: sort, index, density solve and the error
+// statistics of THIS rank's slice.  Unless TG_WVT_SEQUENTIAL is set the displacement is
+// computed in the same sweep with `step_guess` (the step as it stands before this
+// iteration's `step *= 0.8` decision, wvt_relax.c:100) and rescaled by tg_wvt_finish.
+extern "C" int tg_wvt_begin(tg_ctx *c, double step_guess, double *err_sum, double *err_max, int *count)
 {
     if (!c) return TG_EINVAL;
     CU(cudaSetDevice(c->cfg.device));
     int rc = reset_counters(c);
     if (rc) return rc;
-    double emax = 0, emean = 0;
     CU(cudaEventRecord(c->ev[0], c->stream));
-    if ((rc = prepare_index(c))) return rc;
+    if ((rc = prepare_index(c))) return rc;                  // wvt_relax.c:67 -> sph.c:15-17
     CU(cudaEventRecord(c->ev[2], c->stream));
     if (c->cfg.flags & TG_WVT_SEQUENTIAL) {
-        if ((rc = density_pass(c))) return rc;
-        if ((rc = displacement_pass(c, step))) return rc;
+        if ((rc = density_pass(c))) return rc;               // sph.c:19-72
     } else {   // one sweep: density solve and displacement share the walk over HBM
-        SweepArgs a = sweep_args(c, step);
+        SweepArgs a = sweep_args(c, step_guess);
         if ((rc = launch_sweep<MODE_DENSITY | MODE_WVT>(c, a))) return rc;
         c->any_cold = false;
     }
     CU(cudaEventRecord(c->ev[3], c->stream));
-    if ((rc = error_pass(c, &emax, &emean))) return rc;
-    if ((rc = move_pass(c))) return rc;
-    CU(cudaEventRecord(c->ev[1], c->stream));
+    c->step_begin = step_guess;
+    double emax = 0, emean = 0;
+    if ((rc = error_pass(c, &emax, &emean))) return rc;      // wvt_relax.c:73-87
     if ((rc = check_flags(c))) return rc;
+    if (err_sum) *err_sum = emean * (c->hi - c->lo);
     if (err_max) *err_max = emax;
-    if (err_mean) *err_mean = emean;
+    if (count) *count = c->hi - c->lo;
+    return TG_OK;
+}
+
+// Second half: displacement with the final step and move (wvt_relax.c:108-214), or, with
+// step_final <= 0, leave the loop as the reference's `break` does: positions stay, the
+// freshly solved Hsml is kept (wvt_relax.c:94-98).
+extern "C" int tg_wvt_finish(tg_ctx *c, double step_final)
+{
+    if (!c) return TG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    int rc;
+    if (step_final <= 0) {
+        if ((rc = carry_state(c))) return rc;
+    } else {
+        double scale = 1.0;
+        if (c->cfg.flags & TG_WVT_SEQUENTIAL) {
+            if ((rc = displacement_pass(c, step_final))) return rc;
+        } else if (step_final != c->step_begin) {
+            scale = step_final / c->step_begin;              // delta is linear in the step
+        }
+        if ((rc = move_pass(c, scale))) return rc;
+    }
+    CU(cudaEventRecord(c->ev[1], c->stream));
     return finish_stats(c, true);
+}
+
+extern "C" int tg_wvt_iteration(tg_ctx *c, double step, double *err_max, double *err_mean)
+{
+    double sum = 0, mx = 0;
+    int cnt = 0;
+    int rc = tg_wvt_begin(c, step, &sum, &mx, &cnt);
+    if (rc) return rc;
+    if (err_max) *err_max = mx;
+    if (err_mean) *err_mean = cnt > 0 ? sum / cnt : 0;
+    return tg_wvt_finish(c, step);
 }
 
 extern "C" int tg_regularise(tg_ctx *c, int max_iters, tg_log_fn log, void *user, int *iters_done)
 {
     if (!c) return TG_EINVAL;
-    CU(cudaSetDevice(c->cfg.device));
+    if (c->cfg.nranks > 1)
+        return fail(c, TG_EINVAL, "tg_regularise needs the global error statistics: with nranks > 1 "
+                                  "drive tg_wvt_begin / tg_wvt_finish and all-reduce in between");
     // wvt_relax.c:46-59
     int it = -1, started = 0;
     double step = 0.0085;
@@ -723,17 +763,11 @@ extern "C" int tg_regularise(tg_ctx *c, int max_iters, tg_log_fn log, void *user
     for (;;) {
         if (it++ >= TG_NUMITER) break;                       // wvt_relax.c:63
         if (it >= max_iters) break;                          // test / bench cut-off
-        if ((rc = reset_counters(c))) return rc;
-        CU(cudaEventRecord(c->ev[0], c->stream));
-        if ((rc = prepare_index(c))) return rc;              // wvt_relax.c:67 -> sph.c:15-17
-        CU(cudaEventRecord(c->ev[2], c->stream));
-        if ((rc = density_pass(c))) return rc;               // sph.c:19-72
-        CU(cudaEventRecord(c->ev[3], c->stream));
+        double errSum = 0, errMax = 0;
+        int cnt = 0;
+        if ((rc = tg_wvt_begin(c, step, &errSum, &errMax, &cnt))) return rc;
         started++;
-
-        double errMax = 0, errMean = 0;
-        if ((rc = error_pass(c, &errMax, &errMean))) return rc;   // wvt_relax.c:73-87
-        if ((rc = check_flags(c))) return rc;
+        const double errMean = errSum / cnt;                 // wvt_relax.c:87
         errDiff = (errLast - errMean) / errMean;             // wvt_relax.c:89
         int stop = log ? log(it, errMax, errMean, errDiff, step, user) : 0;
 
@@ -741,19 +775,13 @@ extern "C" int tg_regularise(tg_ctx *c, int max_iters, tg_log_fn log, void *user
         if (errDiff < 0.01 && it > 25) leave = true;         // wvt_relax.c:94
         if (errDiff < 0 && errDiffLast < 0 && it > 10) leave = true;   // wvt_relax.c:97
         if (leave) {
-            if ((rc = carry_state(c))) return rc;
-            CU(cudaEventRecord(c->ev[1], c->stream));
-            if ((rc = finish_stats(c, true))) return rc;
+            if ((rc = tg_wvt_finish(c, 0))) return rc;
             break;
         }
         if (errDiff < 0.01 && it > 1) step *= 0.8;           // wvt_relax.c:100
         errLast = errMean;
         errDiffLast = errDiff;
-
-        if ((rc = displacement_pass(c, step))) return rc;    // wvt_relax.c:108-171
-        if ((rc = move_pass(c))) return rc;                  // wvt_relax.c:175-214
-        CU(cudaEventRecord(c->ev[1], c->stream));
-        if ((rc = finish_stats(c, true))) return rc;
+        if ((rc = tg_wvt_finish(c, step))) return rc;        // wvt_relax.c:108-214
     }
     if (iters_done) *iters_done = started;
     return TG_OK;

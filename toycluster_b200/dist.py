@@ -42,3 +42,33 @@ def reduce_errors(err_sum: float, err_max: float, count: int, device="cpu"):
     dist.all_reduce(s, op=dist.ReduceOp.SUM)
     dist.all_reduce(m, op=dist.ReduceOp.MAX)
     return m.item(), s[0].item() / s[1].item()
+
+
+def regularise(g, exchange, max_iters=1 << 30, mtotal=1e5, log=None, device="cpu"):
+    """wvt_relax.c:25-225 for one-process-per-GPU runs: the reference's control flow on
+    all-reduced error statistics, around HotPath.wvt_begin / wvt_finish.  ``exchange()``
+    re-assembles the moved slices (allgather_slices on the library's state buffer)."""
+    step = 0.0085
+    if mtotal < 1e5:
+        step /= 2
+    err_last = err_diff_last = float("inf")
+    it, rows = -1, []
+    while True:
+        it += 1
+        if it - 1 >= 64 or it >= max_iters:
+            break
+        s, m, n = g.wvt_begin(step)
+        err_max, err_mean = reduce_errors(s, m, n, device)
+        err_diff = (err_last - err_mean) / err_mean
+        rows.append(dict(it=it, max=err_max, mean=err_mean, diff=err_diff, step=step))
+        stop = bool(log(it, err_max, err_mean, err_diff, step)) if log else False
+        if stop or (err_diff < 0.01 and it > 25) or (err_diff < 0 and err_diff_last < 0 and it > 10):
+            g.wvt_finish(0.0)
+            exchange()
+            break
+        if err_diff < 0.01 and it > 1:
+            step *= 0.8
+        err_last, err_diff_last = err_mean, err_diff
+        g.wvt_finish(step)
+        exchange()
+    return rows
