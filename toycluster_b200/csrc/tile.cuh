@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
 
             // (2) classify every hit, build the separation list, sum the displacement
             int cntA = 0, cntB = 0, cntW = 0;      // cntA, cntW: per-lane until reduced below
+            bool ranges_ok = true;                 // every separation fit for the hoisted divide
             float sx = 0, sy = 0, sz = 0;
             const float Af = (float)A;
             for (int base = 0; base < nU; base += 32) {
@@ -343,6 +344,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 if (MODE & MODE_DENSITY) {
                     if (inB) {
                         double r = pair_r(pi.x, pi.y, pi.z, xj, yj, zj, a.bx.box_d, a.bx.boxhalf_d);
+                        ranges_ok &= fdiv_range_ok(r);
                         if (!inA) r = __longlong_as_double(__double_as_longlong(r) | (1ll << 63));
                         const int pos = cntB + __popc(mB & lt);
                         if (pos < TL_LCAP) rl[pos] = r;
@@ -367,6 +369,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 cntA += __shfl_xor_sync(FULL_MASK, cntA, o);
                 cntW += __shfl_xor_sync(FULL_MASK, cntW, o);
             }
+            ranges_ok = __all_sync(FULL_MASK, ranges_ok);
             __syncwarp();
 
             float h = hA, rho = 0, drho = 0;
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 } else ok = false;                           // a third search: generic path
                 if (ok) {
                     __syncwarp();
-                    ok = find_hsml(a, L, cnt, h, rho, drho, c_evals, c_iters);
+                    ok = find_hsml(a, L, cnt, h, rho, drho, c_evals, c_iters, ranges_ok);
                 }
                 if (!ok) { hand_back(i); continue; }
             }
