@@ -335,15 +335,19 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 const float xj = pj.x, yj = pj.y, zj = pj.z;
                 float dx = fabsf(__fsub_rn(pi.x, xj)), dy = fabsf(__fsub_rn(pi.y, yj)),
                       dz = fabsf(__fsub_rn(pi.z, zj));
-                if (dx > boxhalf) dx = __fsub_rn(dx, box);
-                if (dy > boxhalf) dy = __fsub_rn(dy, box);
-                if (dz > boxhalf) dz = __fsub_rn(dz, box);
+                if (!interior) {       // interior tile: no hit can be a periodic image
+                    if (dx > boxhalf) dx = __fsub_rn(dx, box);
+                    if (dy > boxhalf) dy = __fsub_rn(dy, box);
+                    if (dz > boxhalf) dz = __fsub_rn(dz, box);
+                }
                 const float r2 = sq3_nofma(dx, dy, dz);                          // tree.c:88
                 const bool inA = live && r2 < hA2, inB = live && r2 < hB2, inW = live && r2 < hsw2;
                 const unsigned mB = __ballot_sync(FULL_MASK, inB);
                 if (MODE & MODE_DENSITY) {
                     if (inB) {
-                        double r = pair_r(pi.x, pi.y, pi.z, xj, yj, zj, a.bx.box_d, a.bx.boxhalf_d);
+                        double r = interior
+                            ? pair_r<false>(pi.x, pi.y, pi.z, xj, yj, zj, a.bx.box_d, a.bx.boxhalf_d)
+                            : pair_r<true>(pi.x, pi.y, pi.z, xj, yj, zj, a.bx.box_d, a.bx.boxhalf_d);
                         ranges_ok &= fdiv_range_ok(r);
                         if (!inA) r = __longlong_as_double(__double_as_longlong(r) | (1ll << 63));
                         const int pos = cntB + __popc(mB & lt);
