@@ -251,3 +251,21 @@ def test_full_relaxation_sequential_and_statistical(wl2):
     ha, _ = np.histogram(np.linalg.norm(got["pos"] - centre, axis=1), bins)
     hb, _ = np.histogram(np.linalg.norm(want["pos"] - centre, axis=1), bins)
     assert np.all(np.abs(ha - hb) <= 3 + 4 * np.sqrt(np.maximum(hb, 1)) * 0.2), (ha, hb)
+
+
+def test_substructure_halo_table():
+    """BASELINE config 5: ~70 rows in Global_density_model's table (wvt_relax.c:235-253).
+    rho_model, the WVT hsml and two iterations stay bit-exact with the reference."""
+    w = workloads.make("merger_sub_1e7", n_gas=N_SMALL)
+    assert len(w.halos) == 70
+    start, after, steps, log = _reference_iterations(w, 2)
+    g = tc.HotPath.from_workload(w, flags=tc.WVT_SEQUENTIAL)
+    g.upload(w.pos)
+    for it in range(2):
+        g.wvt_iteration(steps[it])
+        s, o = after[it], g.download()
+        hw, dl = g.wvt_scratch()
+        assert np.array_equal(o["id"], s["id"])
+        for k in ("rho_model", "hsml", "rho", "varhsml", "pos"):
+            assert np.array_equal(o[k], s[k]), (it, k, (o[k] != s[k]).mean())
+        assert np.array_equal(hw, s["hw"]) and np.array_equal(dl, s["delta"])

@@ -8,26 +8,64 @@
 
 // wvt_relax.c:227-256 + setup.c:598-615: max over halos of the beta model with r^4 cut-off,
 // FP64, returned as float. No periodic wrap around the halo centre (the reference has none).
+static __device__ __forceinline__ double halo_density(const Halo &h, double x, double y, double z,
+                                                      double boxhalf)
+{
+    const double dx = __dsub_rn(__dsub_rn(x, h.cx), boxhalf);   // wvt_relax.c:240-242
+    const double dy = __dsub_rn(__dsub_rn(y, h.cy), boxhalf);
+    const double dz = __dsub_rn(__dsub_rn(z, h.cz), boxhalf);
+    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const double r = sqrt(r2);
+    const double q = r / h.rcore, s = r / h.rcut;
+    // setup.c:601-602, product and sum kept un-contracted like the -std=c99 build
+    const double base = __dadd_rn(1.0, __dmul_rn(q, q));
+    const double cut = __dadd_rn(1.0, __dmul_rn(__dmul_rn(__dmul_rn(s, s), s), s));
+    return h.rho0 * pow(base, -3.0 / 2.0 * h.beta) / cut;
+}
+
+// The same profile in fast float arithmetic, good to ~1e-5: only used to decide WHICH halos
+// can hold the maximum, never for the value.
+static __device__ __forceinline__ float halo_density_estimate(const Halo &h, float x, float y, float z,
+                                                              float boxhalf)
+{
+    const float dx = x - (float)h.cx - boxhalf, dy = y - (float)h.cy - boxhalf,
+                dz = z - (float)h.cz - boxhalf;
+    const float r2 = dx * dx + dy * dy + dz * dz;
+    const float rc = (float)h.rcore, rt = (float)h.rcut;
+    const float s2 = r2 / (rt * rt);
+    return (float)h.rho0 * __powf(1.f + r2 / (rc * rc), -1.5f * (float)h.beta) / (1.f + s2 * s2);
+}
+
 static __device__ __forceinline__ float global_density_model(float xf, float yf, float zf,
                                                              const Halo *__restrict__ halos,
                                                              int nhalos, double boxhalf)
 {
     const double x = xf, y = yf, z = zf;
     double rho = 0;
+    if (nhalos <= 3) {
+        for (int i = 0; i < nhalos; i++) {
+            const Halo h = halos[i];
+            if (h.mass_gas == 0) continue;                   // wvt_relax.c:237
+            rho = fmax(halo_density(h, x, y, z, boxhalf), rho);
+        }
+        return (float)rho;
+    }
+    // Substructure runs carry ~70 rows (substructure.c:127).  The result is a maximum, so the
+    // FP64 pow is only needed for rows whose float estimate is within 1e-3 of the best
+    // estimate (the estimate is good to ~1e-5): same value, ~1 pow per particle instead of 70.
+    const float bh = (float)boxhalf;
+    float best = 0;
     for (int i = 0; i < nhalos; i++) {
         const Halo h = halos[i];
-        if (h.mass_gas == 0) continue;                   // wvt_relax.c:237
-        const double dx = __dsub_rn(__dsub_rn(x, h.cx), boxhalf);   // wvt_relax.c:240-242
-        const double dy = __dsub_rn(__dsub_rn(y, h.cy), boxhalf);
-        const double dz = __dsub_rn(__dsub_rn(z, h.cz), boxhalf);
-        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        const double r = sqrt(r2);
-        const double q = r / h.rcore, s = r / h.rcut;
-        // setup.c:601-602, product and sum kept un-contracted like the -std=c99 build
-        const double base = __dadd_rn(1.0, __dmul_rn(q, q));
-        const double cut = __dadd_rn(1.0, __dmul_rn(__dmul_rn(__dmul_rn(s, s), s), s));
-        const double rho_i = h.rho0 * pow(base, -3.0 / 2.0 * h.beta) / cut;
-        rho = fmax(rho_i, rho);
+        if (h.mass_gas == 0) continue;
+        best = fmaxf(best, halo_density_estimate(h, xf, yf, zf, bh));
+    }
+    const float cut = best * 0.999f;
+    for (int i = 0; i < nhalos; i++) {
+        const Halo h = halos[i];
+        if (h.mass_gas == 0) continue;
+        if (!(halo_density_estimate(h, xf, yf, zf, bh) < cut))
+            rho = fmax(halo_density(h, x, y, z, boxhalf), rho);
     }
     return (float)rho;
 }

@@ -104,8 +104,16 @@ def _mass_table(rho0, beta, rc, rcut, rmax, ntab=1024, sub=64):
 
 def derive(n_gas: int, mass_ratio: float, mtot200: float = 1e5, redshift: float = 0.87,
            bf: float = 0.17, beta: float = 0.54, impact_param: float = 50.0,
-           name: str = "") -> Workload:
-    """Halo table and scalars for a one- or two-cluster system, without positions."""
+           name: str = "", n_sub: int = 0) -> Workload:
+    """Halo table and scalars for a one- or two-cluster system, without positions.
+
+    ``n_sub`` > 0 appends that many subhalo rows to the table (BASELINE config 5).  They are a
+    synthetic stand-in for substructure.c:116-183 (Giocoli mass-function sampling, which is
+    host set-up outside the hot path): the -DADD_THIRD_SUBHALO halo of cluster.par:46
+    (1e12 Msol at the origin) followed by masses log-uniform in [1e12, 2e13] Msol placed
+    uniformly inside R200 of the main halo, each with the main halos' closed-form profile
+    parameters.  What the hot path sees is what matters: a Global_density_model table of
+    ~70 rows and strong density contrast."""
     h100, om, ol = 0.7, 0.3, 0.7                                   # cosmo.c:11-13
     h0_cgs = 100 * h100 * 1e5 / 1000 / _KPC
     ez = math.sqrt(ol + (1 - om - ol) * (1 + redshift) ** 2 + om * (1 + redshift) ** 3)
@@ -116,6 +124,13 @@ def derive(n_gas: int, mass_ratio: float, mtot200: float = 1e5, redshift: float 
     nh = 1 if mass_ratio == 0 else 2
     m200 = [mtot200 / (1 + mass_ratio), 0.0]
     m200[1] = mtot200 - m200[0]
+    n_main = nh
+    sub_pos = []
+    if n_sub > 0:
+        rng = np.random.default_rng(68)                       # substructure.c:127: <= 68 subhalos
+        m200 = m200[:nh] + [100.0] + list(np.exp(rng.uniform(math.log(100.0), math.log(2000.0),
+                                                            n_sub - 1)))
+        nh += n_sub
 
     r200, a_hq, rs = [], [], []
     for i in range(nh):
@@ -145,12 +160,23 @@ def derive(n_gas: int, mass_ratio: float, mtot200: float = 1e5, redshift: float 
                              rcut=rcut, cuspy=0, mass_gas=float(mass_gas), r200=r200[i],
                              r_sample_gas=rs_gas))
 
-    if nh == 2:
+    if n_sub > 0:
+        c0 = np.array(halos[0].dcom)
+        for k in range(n_sub):
+            if k == 0:
+                off = np.zeros(3)                              # SubFirstPos = 0 (cluster.par:48-50)
+            else:
+                v = rng.normal(size=3)
+                off = v / np.linalg.norm(v) * r200[0] * rng.random() ** (1 / 3)
+            sub_pos.append(off)
+    if n_main == 2:
         d = 0.9 * (r200[0] + r200[1])
         x0 = -m200[1] * d / mtot200
         y0 = -m200[1] * impact_param / mtot200
         halos[0].dcom = (x0, y0, 0.0)
         halos[1].dcom = (d + x0, impact_param + y0, 0.0)
+    for k, off in enumerate(sub_pos):                          # subhalos ride with the main halo
+        halos[n_main + k].dcom = tuple(float(v) for v in np.array(halos[0].dcom) + off)
 
     mgas_tot = sum(h.mass_gas for h in halos)
     mpart = mgas_tot / n_gas
@@ -217,6 +243,7 @@ CONFIGS = {
     "single_1e5": dict(n_gas=100_000, mass_ratio=0.0),     # configs[0]: shipped cluster.par
     "merger_1e6": dict(n_gas=1_000_000, mass_ratio=0.3125),  # configs[1]
     "merger_1e7": dict(n_gas=10_000_000, mass_ratio=0.3125),  # configs[2]
+    "merger_sub_1e7": dict(n_gas=10_000_000, mass_ratio=0.3125, n_sub=68),  # configs[4]
 }
 
 
