@@ -277,19 +277,30 @@ def main():
         sync_all()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            g.upload(pos_np, hsml_np)                        # H2D from pinned memory
+            if world == 1:
+                g.upload(pos_np, hsml_np)                    # H2D from pinned memory
+            else:                                            # each rank ships only its slice
+                cold = g.upload_slice(pos_np, hsml_np)
+                exchange()
+                flag = torch.tensor([int(cold)], device="cuda")
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                g.set_cold(bool(flag.item()))
             g.wvt_iteration(step)
             exchange()
-            if world > 1:
+            if world == 1:
+                g.lib.tg_download_soa(g._ctx, pos_np.ctypes.data, None, hsml_np.ctypes.data,
+                                      None, None, None, None)   # D2H of the step's result
+            else:
                 torch.cuda.synchronize()
-            g.lib.tg_download_soa(g._ctx, pos_np.ctypes.data, None, hsml_np.ctypes.data,
-                                  None, None, None, None)   # D2H of the step's result
+                g.download_slice(pos_np, hsml_np)            # D2H of this rank's slice
         sync_all()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": args.steps / dt.item(), "unit": "steps/s",
-               "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
+        final = g.download()                                 # after the exchange every rank holds it all
+        checksum = float(final["pos"].astype(np.float64).sum()) + float(final["hsml"].astype(np.float64).sum())
+        e2e = {"value": args.steps / dt.item(), "unit": "steps/s", "state_checksum": checksum,
+               "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,   # summed over ranks
                "ms_per_step": dt.item() * 1e3 / args.steps}
 
     full = None

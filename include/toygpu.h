@@ -99,6 +99,12 @@ int tg_upload(tg_ctx *ctx, const void *P, size_t p_stride, const void *SphP, siz
 /* Same from plain arrays: pos[n][3]; hsml[n] or NULL (cold start, SphP.Hsml == 0). */
 int tg_upload_soa(tg_ctx *ctx, const float *pos, const float *hsml);
 int tg_set_apot(tg_ctx *ctx, const float *apot /* [n][3], upload order */);
+/* Multi-rank variants: pos/hsml are the FULL arrays but only this rank's slice crosses PCIe.
+ * After tg_upload_soa_slice the host all-gathers pos_hsml_dev (tg_get_exchange) and passes
+ * the OR of every rank's *cold to tg_set_cold. */
+int tg_upload_soa_slice(tg_ctx *ctx, const float *pos, const float *hsml, int *cold);
+int tg_set_cold(tg_ctx *ctx, int any_cold);
+int tg_download_soa_slice(tg_ctx *ctx, float *pos, float *hsml);
 
 /* Writes the path's post-state back into the driver's records: the gas range of P and
  * SphP permuted into the Peano order of the last density call (peano.c:85-126 moves whole

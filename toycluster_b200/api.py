@@ -67,7 +67,7 @@ _LOG_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_
 
 EXPORTS = [
     "tg_create", "tg_destroy", "tg_last_error", "tg_set_halos", "tg_upload", "tg_upload_soa",
-    "tg_set_apot", "tg_download", "tg_download_soa", "tg_find_sph_quantities", "tg_regularise",
+    "tg_upload_soa_slice", "tg_set_cold", "tg_download_soa_slice", "tg_set_apot", "tg_download", "tg_download_soa", "tg_find_sph_quantities", "tg_regularise",
     "tg_bfld_from_rotA", "tg_wvt_iteration", "tg_wvt_begin", "tg_wvt_finish", "tg_wvt_scratch", "tg_get_stats", "tg_peano_keys",
     "tg_sort", "tg_find_ngb", "tg_guess_hsml", "tg_get_exchange",
 ]
@@ -104,6 +104,9 @@ def load():
     lib.tg_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
     lib.tg_upload_soa.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tg_set_apot.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tg_upload_soa_slice.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    lib.tg_set_cold.argtypes = [C.c_void_p, C.c_int]
+    lib.tg_download_soa_slice.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tg_download_soa.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     lib.tg_find_sph_quantities.argtypes = [C.c_void_p]
     lib.tg_regularise.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
@@ -180,6 +183,23 @@ class HotPath:
             hsml = np.ascontiguousarray(hsml, dtype=np.float32)
             assert hsml.shape == (self.n,)
         self._check(self.lib.tg_upload_soa(self._ctx, _ptr(pos), _ptr(hsml)))
+
+    def upload_slice(self, pos, hsml=None) -> bool:
+        """Multi-rank upload of this rank's slice only; returns the slice's cold flag.  The
+        caller all-gathers the state buffer and calls set_cold(any rank cold)."""
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        if hsml is not None:
+            hsml = np.ascontiguousarray(hsml, dtype=np.float32)
+        cold = C.c_int(0)
+        self._check(self.lib.tg_upload_soa_slice(self._ctx, _ptr(pos), _ptr(hsml), C.byref(cold)))
+        return bool(cold.value)
+
+    def set_cold(self, any_cold: bool):
+        self._check(self.lib.tg_set_cold(self._ctx, int(bool(any_cold))))
+
+    def download_slice(self, pos, hsml):
+        """Write this rank's slice of (pos, Hsml) into the full host arrays."""
+        self._check(self.lib.tg_download_soa_slice(self._ctx, _ptr(pos), _ptr(hsml)))
 
     def upload_records(self, P, SphP):
         """AoS records as the C driver holds them (numpy structured or raw byte arrays)."""

@@ -240,3 +240,9 @@ __global__ void k_unpack_state(int n, const float4 *__restrict__ posh, float *__
     pos[3 * (size_t)k] = p.x; pos[3 * (size_t)k + 1] = p.y; pos[3 * (size_t)k + 2] = p.z;
     hsml[k] = p.w;
 }
+
+__global__ void k_iota(int n, int *__restrict__ id)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) id[k] = k;
+}

@@ -374,6 +374,59 @@ extern "C" int tg_upload_soa(tg_ctx *c, const float *pos, const float *hsml)
     return upload_common(c, pos, hsml);
 }
 
+// Multi-rank upload: pos/hsml are the FULL host arrays, but only this rank's slice [lo, hi) is
+// copied (PCIe carries n/nranks records per rank); the host then re-assembles the state buffer
+// with the same all-gather it uses every step and agrees on the cold flag (tg_set_cold).
+extern "C" int tg_upload_soa_slice(tg_ctx *c, const float *pos, const float *hsml, int *cold_out)
+{
+    if (!c || !pos) return fail(c, TG_EINVAL, "tg_upload_soa_slice: null argument");
+    const int n = c->n, lo = c->lo, m = c->hi - c->lo;
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaMemsetAsync(c->flags + 4, 0, sizeof(int), c->stream));
+    if (m > 0) {
+        CU(cudaMemcpyAsync(c->stage, pos + 3 * (size_t)lo, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, c->stream));
+        if (hsml)
+            CU(cudaMemcpyAsync(c->stage + 3 * (size_t)n, hsml + lo, sizeof(float) * m, cudaMemcpyHostToDevice, c->stream));
+        k_pack_state<<<cdiv(m, 256), 256, 0, c->stream>>>(m, c->stage, hsml ? c->stage + 3 * (size_t)n : nullptr,
+                                                         c->posh + lo, c->id + lo, c->flags + 4);
+        LAUNCH_CHECK();
+    }
+    k_iota<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->id);
+    LAUNCH_CHECK();
+    int cold = 0;
+    CU(cudaMemcpyAsync(&cold, c->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->any_cold = cold != 0;
+    c->index_valid = false;
+    c->have_apot = false;
+    CU(cudaMemsetAsync(c->rm_state, 0, sizeof(float) * n, c->stream));
+    if (cold_out) *cold_out = cold;
+    return TG_OK;
+}
+
+extern "C" int tg_set_cold(tg_ctx *c, int any_cold)
+{
+    if (!c) return TG_EINVAL;
+    c->any_cold = any_cold != 0;
+    return TG_OK;
+}
+
+// Read back this rank's slice of (pos, Hsml) into the FULL host arrays.
+extern "C" int tg_download_soa_slice(tg_ctx *c, float *pos, float *hsml)
+{
+    if (!c) return TG_EINVAL;
+    CU(cudaSetDevice(c->cfg.device));
+    const int n = c->n, lo = c->lo, m = c->hi - c->lo;
+    if (m > 0 && (pos || hsml)) {
+        k_unpack_state<<<cdiv(m, 256), 256, 0, c->stream>>>(m, c->posh + lo, c->stage, c->stage + 3 * (size_t)n);
+        LAUNCH_CHECK();
+        if (pos) CU(cudaMemcpyAsync(pos + 3 * (size_t)lo, c->stage, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, c->stream));
+        if (hsml) CU(cudaMemcpyAsync(hsml + lo, c->stage + 3 * (size_t)n, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return TG_OK;
+}
+
 extern "C" int tg_upload(tg_ctx *c, const void *P, size_t p_stride, const void *SphP, size_t s_stride)
 {
     if (!c || !P || !SphP || p_stride < 12 || s_stride < 12)
