@@ -147,3 +147,40 @@ def test_records_travel_with_the_particle():
     assert np.array_equal(S["VarHsmlFac"], o["varhsml"]) and np.array_equal(S["Rho_Model"], o["rho_model"])
     key = (P["Key"][:, 1].astype(object) << 64) | P["Key"][:, 0].astype(object)
     assert all(key[k] < key[k + 1] for k in range(n - 1))       # Peano order of the last sort
+
+
+def test_error_paths_and_edges():
+    """Failure is loud (status + message), like the reference's Assert (aux.c:57-83)."""
+    w = workloads.make("merger_1e6", n_gas=5000)
+    # fewer gas particles than DESNNGB in reach: sph.c:36-64 would spin forever
+    few = tc.HotPath(200, w.boxsize, w.mpart_gas, w.mtotal, w.halo_table())
+    few.upload(w.pos[:200])
+    with pytest.raises(tc.ToyGpuError, match="did not terminate"):
+        few.find_sph_quantities()
+    # a coordinate outside [0, Boxsize]: peano.c:130-132 asserts
+    bad = w.pos.copy()
+    bad[17, 1] = np.float32(w.boxsize * 1.5)
+    g = tc.HotPath.from_workload(w)
+    g.upload(bad)
+    with pytest.raises(tc.ToyGpuError, match="outside"):
+        g.find_sph_quantities()
+    # no halo table / no index / no Apot
+    h = tc.HotPath.from_workload(w)
+    h.upload(w.pos)
+    with pytest.raises(tc.ToyGpuError, match="index"):
+        h.bfld_from_rotA_sph()
+    # x == Boxsize exactly is legal (wvt_relax.c:200 leaves it) and keeps its odd key
+    edge = w.pos.copy()
+    edge[5] = (np.float32(w.boxsize), np.float32(0.3 * w.boxsize), np.float32(0.3 * w.boxsize))
+    g2 = tc.HotPath.from_workload(w)
+    g2.upload(edge)
+    hi, lo = g2.peano_keys()
+    from oracle import port
+    assert (int(hi[5]), int(lo[5])) == port.peano_key(1.0, float(edge[5, 1]) / w.boxsize,
+                                                      float(edge[5, 2]) / w.boxsize)
+    g2.find_sph_quantities()
+    want = port.find_sph_quantities(w, edge)
+    got = g2.download()
+    assert np.array_equal(got["id"], want["id"])
+    for k in ("hsml", "rho", "varhsml"):
+        assert np.array_equal(got[k], want[k]), k

@@ -295,26 +295,41 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
             const float hA2 = __fmul_rn(hA, hA), hB2 = __fmul_rn(hB, hB), hsw2 = __fmul_rn(hsw, hsw);
             const double A = a.step * (double)hi_w;
 
-            // (1) expand the bit row into a compact, ascending candidate-slot list
-            int nU = 0;
-            for (int base = 0; base < ng; base += 32) {
-                const int q = base + lane;
-                unsigned word = q < ng ? s_mask[q * TL_MSTRIDE + tsel] : 0u;
-                const int c = __popc(word);
-                int incl = c;
+            // (1) expand the bit row into a compact candidate-slot list.  Every lane owns the
+            //     words lane, lane+32, ... of the row and writes their hits to one contiguous
+            //     stretch (order inside the list is irrelevant: all sums below are trees), so
+            //     the divergent bit loop runs max-over-lanes(total hits), not sum-of-maxima.
+            unsigned wd[TL_WORDS / 32];
+            int c = 0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(FULL_MASK, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                int off = nU + incl - c;
-                nU += __shfl_sync(FULL_MASK, incl, 31);
-                if (nU <= TL_UCAP) {
-                    while (word) {
-                        const unsigned low = word & (0u - word);
-                        word ^= low;
-                        ul[off++] = (unsigned short)(q * 32 + s_bit[(low * 0x077CB531u) >> 27]);
+            for (int j = 0; j < TL_WORDS / 32; j++) {
+                const int q = j * 32 + lane;
+                wd[j] = q < ng ? s_mask[q * TL_MSTRIDE + tsel] : 0u;
+                c += __popc(wd[j]);
+            }
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int nU = __shfl_sync(FULL_MASK, incl, 31);
+            if (nU <= TL_UCAP) {
+                // one loop body for all of a lane's words (a shift register of words), so
+                // lanes working on different words still issue together
+                static_assert(TL_WORDS / 32 == 4, "word shift register below is written for 4");
+                int off = incl - c, qbase = lane * 32, left = TL_WORDS / 32;
+                unsigned word = wd[0], w1 = wd[1], w2 = wd[2], w3 = wd[3];
+                for (;;) {
+                    if (word == 0) {
+                        if (--left == 0) break;
+                        word = w1; w1 = w2; w2 = w3; w3 = 0;
+                        qbase += 32 * 32;
+                        continue;
                     }
+                    const unsigned low = word & (0u - word);
+                    word ^= low;
+                    ul[off++] = (unsigned short)(qbase + s_bit[(low * 0x077CB531u) >> 27]);
                 }
             }
             if (nU > TL_UCAP) { hand_back(i); continue; }
