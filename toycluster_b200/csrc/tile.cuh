@@ -317,13 +317,16 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
             if (nU <= TL_UCAP) {
                 // one loop body for all of a lane's words (a shift register of words), so
                 // lanes working on different words still issue together
-                static_assert(TL_WORDS / 32 == 4, "word shift register below is written for 4");
-                int off = incl - c, qbase = lane * 32, left = TL_WORDS / 32;
-                unsigned word = wd[0], w1 = wd[1], w2 = wd[2], w3 = wd[3];
+                constexpr int NW = TL_WORDS / 32;
+                int off = incl - c, qbase = lane * 32, left = NW;
+                unsigned word = wd[0];
                 for (;;) {
                     if (word == 0) {
                         if (--left == 0) break;
-                        word = w1; w1 = w2; w2 = w3; w3 = 0;
+#pragma unroll
+                        for (int j = 0; j + 1 < NW; j++) wd[j] = wd[j + 1];   // registers: shift down
+                        wd[NW - 1] = 0;
+                        word = wd[0];
                         qbase += 32 * 32;
                         continue;
                     }
