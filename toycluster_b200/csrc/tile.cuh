@@ -8,20 +8,32 @@
 //
 //   k_tile_walk   one warp per tile: R = max over the tile of the largest radius any of its
 //                 targets can need without a third search (1.23*Hsml, sph.c:51, and the WVT
-//                 radius, wvt_relax.c:135); ordered walk with a box-to-box distance test
-//                 -> ascending list of candidate boxes in global memory.
-//   k_sweep_tile  one 8-warp block per tile:
+//                 radius, wvt_relax.c:135); ordered walk with a box-to-box distance test, at
+//                 the leaves run-against-run on 8-particle sub-boxes -> ascending list of
+//                 (box, run mask) entries in global memory (~370 runs = 2900 candidates).
+//   k_sweep_tile  one 8-warp block per tile, 3 blocks per SM:
 //     phase 1  one LANE per TARGET, all lanes read the same candidate (one broadcast 16-byte
-//              load per candidate, served by L1/L2): the exact float predicate of
-//              tree.c:67-88 for radius R_i -> one bit per (target, candidate) in a
-//              shared-memory bit matrix.  No divergence, no ballots, no per-target walk.
-//     phase 2  one WARP per target: expand the target's bit row into a compact candidate
-//              list, classify each hit against Hsml, 1.23*Hsml and the WVT radius, build the
-//              FP64 separation list with full lanes, run Find_hsml (sph.c:80-214) and the
-//              displacement sum (wvt_relax.c:137-170) -- all with the same arithmetic as v1.
+//              load per candidate, served by L1/L2): an FMA-contracted SUPERSET of the float
+//              predicate of tree.c:67-88 at radius R_i -> one bit per (target, candidate) in
+//              a shared-memory bit matrix.  No divergence, no ballots, no per-target walk.
+//     phase 2  one WARP per target: expand the target's bit row into a compact hit list,
+//              re-evaluate every hit with the exact FMA-free predicate against Hsml,
+//              1.23*Hsml and the WVT radius, build the FP64 separation list with full lanes,
+//              run Find_hsml (sph.c:80-214) and the displacement sum (wvt_relax.c:137-170)
+//              -- the same device functions as the generic sweep.
 //   Anything outside the fast path's envelope (cold start, list overflow, a third search,
 //   Find_hsml not converging on the frozen list) is pushed to a work list and redone from
-//   scratch by the generic v1 kernel, so results do not depend on which path ran.
+//   scratch by the generic kernel, so results do not depend on which path ran
+//   (tests/test_gpu_golden.py::test_tile_path_equals_generic_path).
+//
+// Tuning record (B200, 1 M-particle merger, sweep ms; see profiles/):
+//   v1 generic 25.4 | tiles, 2 blocks/SM 22.8 | + hoisted divide, 2-way ILP, FMA prefilter,
+//   aliased lists, 3 blocks/SM 14.7 | + sub-box walk 14.0 | + XU relief 13.3 | + exact u-clamp,
+//   interior tiles 12.8.  Tried and dropped: 4 blocks/SM with the list tail in global memory
+//   (13.2: the register cap and the split accessor cost more than the occupancy gains),
+//   larger caps 640 runs / 768 hits (13.3: fewer hand-backs but a smaller L1 carve-out),
+//   smaller caps (13.2-15.3: hand-backs), software-pipelined candidate fetch (13.1),
+//   per-sub-run candidate lists (only 23 % fewer candidates for a second bit matrix).
 #pragma once
 #include "common.cuh"
 #include "bvh.cuh"
