@@ -40,6 +40,9 @@ def lib():
         _lib = C.CDLL(LIB)
         _lib.to_find_ngb.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_int, C.c_float,
                                      C.c_void_p]
+        _lib.to_find_ngb_simple.argtypes = _lib.to_find_ngb.argtypes
+        _lib.to_tree_displaced.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_void_p,
+                                           C.c_void_p, C.c_int]
         _lib.to_sort.argtypes = [C.c_int, C.c_void_p, C.c_double] + [C.c_void_p] * 3
         _lib.to_peano_key.argtypes = [C.c_double] * 3 + [C.c_int, C.POINTER(C.c_uint64),
                                                          C.POINTER(C.c_uint64)]
@@ -89,6 +92,25 @@ def find_ngb(pos, box, i, h):
     out = np.empty(NGBMAX, np.int32)
     cnt = lib().to_find_ngb(len(pos), _p(pos), float(box), int(i), float(h), _p(out))
     return out[:cnt].copy()
+
+
+def find_ngb_simple(pos, box, i, h):
+    """wvt_relax.c:296-340 (Find_ngb_simple): the predicate without the tree."""
+    pos = np.ascontiguousarray(pos, np.float32)
+    out = np.empty(NGBMAX, np.int32)
+    cnt = lib().to_find_ngb_simple(len(pos), _p(pos), float(box), int(i), float(h), _p(out))
+    return out[:cnt].copy()
+
+
+def tree_displaced(pos_sorted, box, cap=4096):
+    """Leaves of the reference octree whose particles lie outside the node's cube (centre
+    displaced by the sign test of tree.c:298-302) -> (first particle, count) per leaf."""
+    pos_sorted = np.ascontiguousarray(pos_sorted, np.float32)
+    first, count = np.empty(cap, np.int32), np.empty(cap, np.int32)
+    m = lib().to_tree_displaced(len(pos_sorted), _p(pos_sorted), float(box), _p(first),
+                                _p(count), cap)
+    m = min(m, cap)
+    return first[:m].copy(), count[:m].copy()
 
 
 def guess_hsml(pos_sorted, box):

@@ -7,9 +7,10 @@
  * Plain C99 on explicit arrays (no globals), written from the reference's behaviour:
  *   peano.c:128-203, 211-284   Hilbert keys             -> to_peano_key, to_reversed_key
  *   peano.c:46-126 + sort.c    key sort + reorder       -> to_sort (ties by index, see below)
- *   tree.c:25-111              neighbour predicate      -> to_find_ngb (the PREDICATE and the
- *                              ascending / first-2360 contract; the walk itself is a cell grid)
- *   tree.c:113-271             Guess_hsml via the sequential octree build -> to_guess_hsml
+ *   tree.c:124-357             the sequential octree build, node centres included -> tree_build
+ *   tree.c:25-111              the depth-first walk, its open test and the particle predicate
+ *                              -> find_ngb / to_find_ngb (ascending, first 2360)
+ *   tree.c:113-121             Guess_hsml -> to_guess_hsml
  *   sph.c:13-214, 426-440      density / hsml solve     -> to_find_sph_quantities
  *   wvt_relax.c:61-256         one WVT iteration + the control loop -> to_wvt_iteration,
  *                              to_regularise
@@ -150,122 +151,64 @@ static inline int near_f32(const float *pi, const float *pj, float h, float box,
     return dx * dx + dy * dy + dz * dz < h * h;
 }
 
+/* The reference's search index, restated in full: the sequentially built octree of
+ * tree.c:124-271 (nodes in depth-first order; `node + 1` is the first child, DNext skips a
+ * finished subtree, DNext < 0 marks a leaf whose first particle is -DNext-1) and the walk of
+ * tree.c:25-111.  The walk is part of the contract, not only its particle predicate: a node's
+ * centre is placed by comparing the position of the particle that creates it with the centre
+ * of the parent (tree.c:298-310), while membership is decided by key triplets.  A particle
+ * lying exactly on a centre plane of its parent cell (or within the float rounding of a deep
+ * centre) is a member of the upper cell but `Pos > centre` is false, so the node -- and every
+ * descendant, whose centres derive from it -- is displaced by one cell size, and the open
+ * test of tree.c:56-58 then prunes particles that are within reach.  ~8 nodes per 1e6
+ * particles in the merger workloads; the neighbour sets, and through them rho / hsml / the
+ * displacements, are the reference's only if this is reproduced. */
+typedef struct { int level, triplet, npart, dnext; float pos[3], size; } tnode;
 typedef struct {
-    int n, nc;          /* particles, cells per axis */
+    int n, nn;
     double box;
-    int *start;         /* nc^3 + 1 */
-    int *item;          /* particle indices, ascending inside each cell */
-} grid;
+    tnode *T;
+    int *parent_of;     /* P[i].Tree_Parent */
+} tree;
 
-static int cell_of(const grid *g, float x)
+static void tree_free(tree *t)
 {
-    int c = (int)(x / g->box * g->nc);
-    return c < 0 ? 0 : (c >= g->nc ? g->nc - 1 : c);
+    free(t->T);
+    free(t->parent_of);
+    free(t);
 }
 
-static grid *grid_build(int n, const float *pos, double box)
+/* tree.c:284-317 */
+static void new_node(tree *t, const float *pos, int ip, int par, u128 key3, int lvl)
 {
-    grid *g = malloc(sizeof *g);
-    g->n = n;
-    g->box = box;
-    g->nc = (int)cbrt(n / 8.0);
-    if (g->nc < 1) g->nc = 1;
-    if (g->nc > 128) g->nc = 128;
-    const int ncell = g->nc * g->nc * g->nc;
-    g->start = calloc(ncell + 1, sizeof(int));
-    g->item = malloc((size_t)n * sizeof(int));
-    int *cid = malloc((size_t)n * sizeof(int));
-    for (int i = 0; i < n; i++) {
-        cid[i] = (cell_of(g, pos[3 * i]) * g->nc + cell_of(g, pos[3 * i + 1])) * g->nc +
-                 cell_of(g, pos[3 * i + 2]);
-        g->start[cid[i] + 1]++;
+    tnode *N = &t->T[t->nn++];
+    const tnode *Q = &t->T[par];
+    N->level = lvl;
+    N->triplet = (int)(key3 & 7);
+    N->npart = 1;
+    N->dnext = -ip - 1;
+    const float size = t->box / (1 << lvl);                        /* tree.c:304 */
+    N->size = size;
+    for (int d = 0; d < 3; d++) {
+        const int sign = -1 + 2 * (pos[3 * ip + d] > Q->pos[d]);   /* tree.c:298-302 */
+        N->pos[d] = Q->pos[d] + sign * size * 0.5;                 /* tree.c:308-310 */
     }
-    for (int c = 0; c < ncell; c++) g->start[c + 1] += g->start[c];
-    int *fill = malloc((size_t)ncell * sizeof(int));
-    memcpy(fill, g->start, (size_t)ncell * sizeof(int));
-    for (int i = 0; i < n; i++) g->item[fill[cid[i]]++] = i;
-    free(fill);
-    free(cid);
-    return g;
+    t->parent_of[ip] = par;
 }
 
-static void grid_free(grid *g)
+static tree *tree_build(int n, const float *pos, double box)
 {
-    free(g->start);
-    free(g->item);
-    free(g);
-}
-
-static int cmp_int(const void *a, const void *b)
-{
-    return (*(const int *)a > *(const int *)b) - (*(const int *)a < *(const int *)b);
-}
-
-/* Find_ngb_tree's contract (tree.c:25-111): every j with near_f32, ascending, and only the
- * first NGBMAX of them.  `scratch` must hold n ints. */
-static int find_ngb(const grid *g, const float *pos, int i, float h, int *list, int *scratch)
-{
-    const float box = (float)g->box, boxhalf = (float)(g->box * 0.5);
-    const float *pi = pos + 3 * i;
-    int cnt = 0;
-    const double w = g->box / g->nc;
-    const int reach = (int)(h / w) + 1;
-
-    if (2 * reach + 1 >= g->nc) {            /* radius spans the grid: plain ordered scan */
-        for (int j = 0; j < g->n && cnt < NGBMAX; j++)
-            if (near_f32(pi, pos + 3 * j, h, box, boxhalf)) list[cnt++] = j;
-        return cnt;
-    }
-    const int c0[3] = {cell_of(g, pi[0]), cell_of(g, pi[1]), cell_of(g, pi[2])};
-    int m = 0;
-    for (int a = -reach; a <= reach; a++)
-        for (int b = -reach; b <= reach; b++)
-            for (int c = -reach; c <= reach; c++) {
-                const int ca = ((c0[0] + a) % g->nc + g->nc) % g->nc;
-                const int cb = ((c0[1] + b) % g->nc + g->nc) % g->nc;
-                const int cc = ((c0[2] + c) % g->nc + g->nc) % g->nc;
-                const int cell = (ca * g->nc + cb) * g->nc + cc;
-                for (int k = g->start[cell]; k < g->start[cell + 1]; k++) {
-                    const int j = g->item[k];
-                    if (near_f32(pi, pos + 3 * j, h, box, boxhalf)) scratch[m++] = j;
-                }
-            }
-    qsort(scratch, m, sizeof(int), cmp_int);
-    cnt = m < NGBMAX ? m : NGBMAX;
-    memcpy(list, scratch, (size_t)cnt * sizeof(int));
-    return cnt;
-}
-
-int to_find_ngb(int n, const float *pos, double box, int i, float h, int *list)
-{
-    grid *g = grid_build(n, pos, box);
-    int *scratch = malloc((size_t)n * sizeof(int));
-    const int cnt = find_ngb(g, pos, i, h, list, scratch);
-    free(scratch);
-    grid_free(g);
-    return cnt;
-}
-
-/* ------------------------------------------------------------------ Guess_hsml (tree.c) */
-
-/* The sequential octree build of tree.c:124-236, reduced to what Guess_hsml reads: for each
- * particle the level and particle count of its Tree_Parent node.  Nodes are kept in
- * depth-first order exactly like the reference (so `node + 1` is the first child and DNext
- * skips a finished subtree), but only {level, triplet, npart, dnext} are stored. */
-typedef struct { int level, triplet, npart, dnext; } tnode;
-
-static void tree_parents(int n, const float *pos, double box, int *plevel, int *pcount)
-{
+    tree *t = malloc(sizeof *t);
     const int maxn = (int)(n * 0.7) + 64;        /* tree.c:3,341 */
-    tnode *T = calloc(maxn, sizeof *T);
-    int *parent_of = malloc((size_t)n * sizeof(int));
-    int nn = 0;
+    t->n = n;
+    t->box = box;
+    t->nn = 0;
+    t->T = calloc(maxn, sizeof *t->T);
+    t->parent_of = malloc((size_t)n * sizeof(int));
+    tnode *T = t->T;
 
-#define NEW_NODE(ip, par, key3, lvl) do { \
-        T[nn].level = (lvl); T[nn].triplet = (int)((key3) & 7); T[nn].npart = 1; \
-        T[nn].dnext = -(ip) - 1; parent_of[ip] = (par); nn++; } while (0)
-
-    NEW_NODE(0, 0, 0, 0);                        /* tree.c:131: root made from particle 0 */
+    new_node(t, pos, 0, 0, 0, 0);                /* tree.c:131: root made from particle 0 */
+    T[0].pos[0] = T[0].pos[1] = T[0].pos[2] = box / 2;             /* tree.c:133 */
     int last_parent = 0;
     u128 last_key = reversed_key((float)(pos[0] / box), (float)(pos[1] / box),
                                  (float)(pos[2] / box)) >> 3;   /* tree.c:137-143 (float!) */
@@ -278,7 +221,7 @@ static void tree_parents(int n, const float *pos, double box, int *plevel, int *
             if ((int)(key & 7) == T[node].triplet) {              /* inside: descend */
                 if (T[node].npart == 1) {                        /* refine (tree.c:163-171) */
                     T[node].dnext = 0;
-                    NEW_NODE(ip - 1, node, last_key, lvl + 1);
+                    new_node(t, pos, ip - 1, node, last_key, lvl + 1);
                     last_key >>= 3;
                 }
                 T[node].npart++;
@@ -288,11 +231,11 @@ static void tree_parents(int n, const float *pos, double box, int *plevel, int *
                 lvl++;
                 key >>= 3;
             } else {                                              /* skip to the sibling */
-                if (T[node].dnext == 0 || node == nn - 1) break;
+                if (T[node].dnext == 0 || node == t->nn - 1) break;
                 node += T[node].dnext > 1 ? T[node].dnext : 1;
             }
         }
-        if (lvl > 41) { parent_of[ip] = parent; continue; }       /* tree.c:194-199 */
+        if (lvl > 41) { t->parent_of[ip] = parent; continue; }    /* tree.c:194-199 */
 
         if (new_branch) {                                          /* tree.c:201-226 */
             int c = 0;
@@ -300,39 +243,135 @@ static void tree_parents(int n, const float *pos, double box, int *plevel, int *
             else if (T[last_parent].npart <= 8) c = last_parent;
             if (c != 0) {
                 T[c].dnext = -ip + T[c].npart - 1;
-                memset(&T[c + 1], 0, (size_t)(nn - c - 1) * sizeof *T);
-                nn = c + 1;
-                for (int j = ip - T[c].npart; j < ip; j++) parent_of[j] = c;
+                memset(&T[c + 1], 0, (size_t)(t->nn - c - 1) * sizeof *T);
+                t->nn = c + 1;
+                for (int j = ip - T[c].npart; j < ip; j++) t->parent_of[j] = c;
             }
         }
-        if (T[node].dnext == 0) T[node].dnext = nn - node;
-        NEW_NODE(ip, parent, key, lvl);
+        if (T[node].dnext == 0) T[node].dnext = t->nn - node;
+        new_node(t, pos, ip, parent, key, lvl);
         last_key = key >> 3;
         last_parent = parent;
-        if (nn >= maxn - 2) break;                                 /* tree.c:287-292 would exit */
+        if (t->nn >= maxn - 2) break;                              /* tree.c:287-292 would exit */
     }
-#undef NEW_NODE
-    for (int i = 0; i < n; i++) {
-        plevel[i] = T[parent_of[i]].level;
-        pcount[i] = T[parent_of[i]].npart;
+
+    T[0].dnext = 0;                                                /* tree.c:238-266 */
+    int stack[43] = {0}, lowest = 0;
+    for (int i = 1; i < t->nn; i++) {
+        const int lvl = T[i].level;
+        while (lvl <= lowest) {
+            const int node = stack[lowest];
+            if (node > 0) T[node].dnext = i - node;
+            stack[lowest] = 0;
+            lowest--;
+        }
+        if (T[i].dnext == 0) { stack[lvl] = i; lowest = lvl; }
     }
-    free(parent_of);
-    free(T);
+    return t;
 }
 
-/* 2*Guess_hsml (sph.c:26, tree.c:113-121) for every particle of a SORTED position array. */
-void to_guess_hsml(int n, const float *pos, double box, float *out)
+/* tree.c:37-58: |d| per axis in float, one wrap, against 0.5*sqrt3*Size + hsml. */
+static inline int node_open(const tnode *N, const float *pi, float h, float box, float boxhalf)
 {
-    int *lvl = malloc((size_t)n * sizeof(int)), *cnt = malloc((size_t)n * sizeof(int));
-    tree_parents(n, pos, box, lvl, cnt);
-    for (int i = 0; i < n; i++) {
-        const float size = box / (1 << lvl[i]);                   /* tree.c:304 */
-        const float numdens = cnt[i] / (size * size * size);      /* tree.c:117 */
-        const float s = pow(FOURPITHIRD / numdens, 1. / 3.);      /* tree.c:118 */
+    float dx = fabsf(pi[0] - N->pos[0]), dy = fabsf(pi[1] - N->pos[1]), dz = fabsf(pi[2] - N->pos[2]);
+    if (dx > boxhalf) dx -= box;
+    if (dy > boxhalf) dy -= box;
+    if (dz > boxhalf) dz -= box;
+    const float dl = 0.5 * SQRT3 * N->size + h;
+    return dx * dx + dy * dy + dz * dz < dl * dl;
+}
+
+/* Find_ngb_tree (tree.c:25-111): depth-first walk from node 1, ascending particle index,
+ * returns as soon as the list holds NGBMAX entries. */
+static int find_ngb(const tree *t, const float *pos, int i, float h, int *list)
+{
+    const float box = (float)t->box, boxhalf = (float)(t->box * 0.5);
+    const float *pi = pos + 3 * i;
+    const tnode *T = t->T;
+    int cnt = 0, node = 1;
+    if (t->nn < 2) {   /* a one-particle "tree": tree.c would read past NNodes; nothing to find */
+        return 0;
+    }
+    for (;;) {
+        if (node_open(&T[node], pi, h, box, boxhalf)) {
+            if (T[node].dnext < 0) {
+                const int first = -(T[node].dnext + 1), last = first + T[node].npart;
+                for (int j = first; j < last; j++) {
+                    if (near_f32(pi, pos + 3 * j, h, box, boxhalf)) list[cnt++] = j;
+                    if (cnt == NGBMAX) return cnt;
+                }
+            }
+            node++;
+            if (node >= t->nn) break;
+            continue;
+        }
+        node += T[node].dnext > 1 ? T[node].dnext : 1;
+        if (node >= t->nn) break;
+    }
+    return cnt;
+}
+
+/* The same contract without the tree: every j with near_f32, ascending, first NGBMAX
+ * (wvt_relax.c:296-340, Find_ngb_simple). */
+int to_find_ngb_simple(int n, const float *pos, double box, int i, float h, int *list)
+{
+    const float boxf = (float)box, boxhalf = (float)(box * 0.5);
+    int cnt = 0;
+    for (int j = 0; j < n && cnt < NGBMAX; j++)
+        if (near_f32(pos + 3 * i, pos + 3 * j, h, boxf, boxhalf)) list[cnt++] = j;
+    return cnt;
+}
+
+int to_find_ngb(int n, const float *pos, double box, int i, float h, int *list)
+{
+    tree *t = tree_build(n, pos, box);
+    const int cnt = find_ngb(t, pos, i, h, list);
+    tree_free(t);
+    return cnt;
+}
+
+/* Number of nodes of the tree whose centre is not the centre of their key cell (diagnostic
+ * for tests): a node is displaced when the sign test of tree.c:298-302 disagreed with the
+ * cell the key put the particle in, or when an ancestor is displaced. */
+int to_tree_displaced(int n, const float *pos, double box, int *node_first, int *node_count, int cap)
+{
+    tree *t = tree_build(n, pos, box);
+    int found = 0;
+    for (int k = 1; k < t->nn; k++) {
+        const tnode *N = &t->T[k];
+        if (N->dnext >= 0) continue;                 /* leaves carry the particles */
+        const int first = -(N->dnext + 1);
+        int out = 0;
+        for (int j = first; j < first + N->npart && !out; j++)
+            for (int d = 0; d < 3; d++)
+                if (fabsf(pos[3 * j + d] - N->pos[d]) > 0.5001f * N->size) out = 1;
+        if (out) {
+            if (found < cap) { node_first[found] = first; node_count[found] = N->npart; }
+            found++;
+        }
+    }
+    tree_free(t);
+    return found;
+}
+
+/* ------------------------------------------------------------------ Guess_hsml (tree.c) */
+
+/* 2*Guess_hsml (sph.c:26, tree.c:113-121) for every particle of a SORTED position array. */
+static void guess_from_tree(const tree *t, float *out)
+{
+    for (int i = 0; i < t->n; i++) {
+        const tnode *N = &t->T[t->parent_of[i]];
+        const float numdens = N->npart / (N->size * N->size * N->size);   /* tree.c:117 */
+        const float s = pow(FOURPITHIRD / numdens, 1. / 3.);              /* tree.c:118 */
         out[i] = 2 * (2 * s);
     }
-    free(lvl);
-    free(cnt);
+}
+
+void to_guess_hsml(int n, const float *pos, double box, float *out)
+{
+    tree *t = tree_build(n, pos, box);
+    guess_from_tree(t, out);
+    tree_free(t);
 }
 
 /* ------------------------------------------------------------------ kernels */
@@ -426,26 +465,26 @@ int to_density(const to_sys *s, const float *pos, float *hsml, float *rho, float
                long *stats)
 {
     const int n = s->n;
-    grid *g = grid_build(n, pos, s->box);
+    tree *g = tree_build(n, pos, s->box);
     float *guess = NULL;
     for (int i = 0; i < n; i++)
         if (hsml[i] == 0) {
             guess = malloc((size_t)n * sizeof(float));
-            to_guess_hsml(n, pos, s->box, guess);
+            guess_from_tree(g, guess);
             break;
         }
     long evals = 0, searches = 0, iters = 0;
     int bad = 0;
     #pragma omp parallel reduction(+ : evals, searches, iters, bad)
     {
-        int *list = malloc(NGBMAX * sizeof(int)), *scratch = malloc((size_t)n * sizeof(int));
+        int *list = malloc(NGBMAX * sizeof(int));
         #pragma omp for schedule(dynamic, 64)
         for (int i = 0; i < n; i++) {
             float h = hsml[i] == 0 ? guess[i] : hsml[i];
             float drho = 0, r = 0;
             int done = 0;
             for (int guard = 0; guard < 4096 && !done; guard++) {
-                const int cnt = find_ngb(g, pos, i, h, list, scratch);
+                const int cnt = find_ngb(g, pos, i, h, list);
                 searches++;
                 if (cnt == NGBMAX) { h /= 1.24; continue; }
                 if (cnt < DESNNGB) { h *= 1.23; continue; }
@@ -457,11 +496,10 @@ int to_density(const to_sys *s, const float *pos, float *hsml, float *rho, float
             varhsml[i] = 1.0 / (1 + h / (3 * r) * drho);          /* sph.c:66 */
         }
         free(list);
-        free(scratch);
     }
     if (stats) { stats[0] += evals; stats[1] += searches; stats[2] += iters; }
     free(guess);
-    grid_free(g);
+    tree_free(g);
     return bad;
 }
 
@@ -518,15 +556,15 @@ void to_wvt_displace(const to_sys *s, float *pos, const float *rho, double step,
     const float norm = pow(DESNNGB / vsum / FOURPITHIRD, 1.0 / 3.0);
     for (int i = 0; i < n; i++) hsml_wvt[i] *= norm;
 
-    grid *g = grid_build(n, pos, box);
+    tree *g = tree_build(n, pos, box);
     long pairs = 0, searches = 0;
     #pragma omp parallel reduction(+ : pairs, searches)
     {
-        int *list = malloc(NGBMAX * sizeof(int)), *scratch = malloc((size_t)n * sizeof(int));
+        int *list = malloc(NGBMAX * sizeof(int));
         #pragma omp for schedule(dynamic, 64)
         for (int i = 0; i < n; i++) {                              /* wvt_relax.c:128-171 */
             float d[3] = {0, 0, 0};
-            const int cnt = find_ngb(g, pos, i, hsml_wvt[i] * box, list, scratch);
+            const int cnt = find_ngb(g, pos, i, hsml_wvt[i] * box, list);
             searches++;
             for (int k = 0; k < cnt; k++) {
                 const int j = list[k];
@@ -555,9 +593,8 @@ void to_wvt_displace(const to_sys *s, float *pos, const float *rho, double step,
             delta[3 * i + 2] = d[2];
         }
         free(list);
-        free(scratch);
     }
-    grid_free(g);
+    tree_free(g);
     if (stats) { stats[0] += pairs; stats[1] += searches; }
 
     for (int i = 0; i < n; i++)                                    /* wvt_relax.c:193-213 */
@@ -577,13 +614,13 @@ void to_bfld_from_rotA(const to_sys *s, const float *pos, const float *hsml, con
 {
     const int n = s->n;
     const double boxhalf = s->box / 2, box = s->box;
-    grid *g = grid_build(n, pos, box);
+    tree *g = tree_build(n, pos, box);
     #pragma omp parallel
     {
-        int *list = malloc(NGBMAX * sizeof(int)), *scratch = malloc((size_t)n * sizeof(int));
+        int *list = malloc(NGBMAX * sizeof(int));
         #pragma omp for schedule(dynamic, 64)
         for (int i = 0; i < n; i++) {
-            const int cnt = find_ngb(g, pos, i, hsml[i], list, scratch);
+            const int cnt = find_ngb(g, pos, i, hsml[i], list);
             const double vf = varhsml[i], h = hsml[i], rho_i = rho[i];
             double b[3] = {0, 0, 0};
             for (int k = 0; k < cnt; k++) {
@@ -612,9 +649,8 @@ void to_bfld_from_rotA(const to_sys *s, const float *pos, const float *hsml, con
             bfld[3 * i + 2] = (float)b[2];
         }
         free(list);
-        free(scratch);
     }
-    grid_free(g);
+    tree_free(g);
 }
 
 /* ------------------------------------------------------------------ reorder helper */
