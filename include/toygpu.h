@@ -43,6 +43,15 @@ enum {
                                  precision (float += double, ascending neighbour index,
                                  wvt_relax.c:167-169) instead of one FP64 tree sum */
 
+#define TG_EXACT_NEIGHBOURS 2u /* do NOT reproduce the reference octree's displaced nodes:
+                                 Find_ngb_tree (tree.c:25-111) places a node's centre by the
+                                 sign test of tree.c:298-302, which disagrees with the key cell
+                                 for a particle lying exactly on a centre plane; the displaced
+                                 subtree is then pruned for targets within reach (~8 nodes,
+                                 ~400 affected targets per 1e6 particles).  Default: reproduced
+                                 bit for bit.  With this flag every search returns the exact
+                                 predicate set (== Find_ngb_simple, wvt_relax.c:296-340) */
+
 /* One row of the table Global_density_model() walks (wvt_relax.c:227-256):
  * Halo[i].{D_CoM, Rho0, Beta, Rcore, Rcut, Have_Cuspy, Mass[0]} (globals.h:128-157). */
 typedef struct {
@@ -81,6 +90,10 @@ typedef struct {
     double step_ms;                  /* device time of the whole step */
     unsigned long long handed_back;  /* targets the tile sweep returned to the generic sweep
                                         (last sweep launch of the step) */
+    unsigned long long displaced_nodes;      /* reference-tree nodes displaced by tree.c:298-302
+                                                in the current index (superset count) */
+    unsigned long long displaced_particles;  /* particles underneath them (carry a path) */
+    unsigned long long displaced_overflow;   /* 1: path table full, some left unreproduced */
 } tg_stats;
 
 /* ---- life cycle -------------------------------------------------------------------- */

@@ -1,0 +1,170 @@
+"""The reference octree displaces a node when the particle that creates it lies exactly on a
+centre plane of the parent cell (tree.c:298-310), and Find_ngb_tree then prunes in-reach
+particles underneath it (tree.c:56-58).  workloads.snap_to_cell_planes makes that common at
+test sizes; these tests pin the restatement (CPU) and libtoygpu (GPU) against the unmodified
+reference on such input."""
+import numpy as np
+import pytest
+
+import toycluster_b200 as tc
+from oracle import port, ref
+from toycluster_b200 import workloads
+
+N = 8192
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+
+
+@pytest.fixture(scope="module")
+def wl():
+    w = workloads.make("merger_1e6", n_gas=N, seed=3)
+    w.pos = workloads.snap_to_cell_planes(w.pos, w.boxsize, 300)
+    return w
+
+
+def _ref(w, threads=4):
+    return ref.Ref(w.n_gas, w.boxsize, w.mpart_gas, w.mtotal, w.halo_table(), threads)
+
+
+@needs_ref
+def test_reference_tree_really_prunes(wl):
+    """The premise: on this input Find_ngb_tree != Find_ngb_simple for many targets."""
+    r = _ref(wl)
+    r.load(wl.pos)
+    r.find_sph_quantities()
+    d = r.read()
+    first, count = port.tree_displaced(d["pos"], wl.boxsize)
+    assert len(first) > 20
+    differ = 0
+    for i in range(0, N, 37):
+        h = float(d["hsml"][i])
+        a, s = r.find_ngb_tree(i, h), r.find_ngb_simple(i, h)
+        assert set(a) <= set(s)
+        differ += len(a) != len(s)
+        assert np.array_equal(port.find_ngb(d["pos"], wl.boxsize, i, h), a)
+        assert np.array_equal(port.find_ngb_simple(d["pos"], wl.boxsize, i, h), s)
+    assert differ > 10
+
+
+@needs_ref
+def test_port_matches_reference_with_displaced_nodes(wl):
+    r = _ref(wl)
+    r.load(wl.pos)
+    snaps = []
+
+    def cb(it):
+        s = r.read()
+        if it > 0:
+            s["hw"], s["delta"] = r.wvt_scratch()
+        snaps.append(s)
+        return 0
+
+    niter = 2
+    r.regularise(niter, cb)
+    rows, state, states = port.regularise(wl, wl.pos, max_iters=niter, keep=True)
+    for it in range(niter):
+        a, b = states[it], snaps[it + 1]
+        assert np.array_equal(a["id"], b["id"])
+        for k in ("hsml", "rho", "varhsml", "rho_model", "hw", "delta", "pos"):
+            assert np.array_equal(a[k], b[k]), (it, k)
+
+
+# ---------------------------------------------------------------------------- GPU
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_gpu_neighbour_sets_follow_the_reference_tree(wl):
+    r = _ref(wl)
+    r.load(wl.pos)
+    r.find_sph_quantities()
+    d = r.read()
+    g = tc.HotPath.from_workload(wl)
+    g.upload(wl.pos)
+    g.sort()
+    st = g.stats()
+    assert st["displaced_nodes"] > 20 and st["displaced_particles"] > 50
+    assert st["displaced_overflow"] == 0
+    e = tc.HotPath.from_workload(wl, flags=tc.EXACT_NEIGHBOURS)
+    e.upload(wl.pos)
+    e.sort()
+    assert e.stats()["displaced_nodes"] == 0
+    differ = 0
+    for i in range(0, N, 23):
+        for h in (float(d["hsml"][i]), float(d["hsml"][i]) * 1.7, 0.2 * wl.boxsize):
+            a = r.find_ngb_tree(i, h)
+            assert np.array_equal(g.find_ngb(i, h), a), (i, h)
+            s = r.find_ngb_simple(i, h)
+            assert np.array_equal(e.find_ngb(i, h), s), (i, h)
+            differ += len(a) != len(s)
+    assert differ > 20
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("tiles", [True, False])
+def test_gpu_iterations_bit_exact_with_displaced_nodes(wl, tiles, monkeypatch):
+    """Cold start + 3 WVT iterations in the reference's accumulation order: every array
+    bit-identical, on the tile path (hand-backs) and on the generic path alone."""
+    if not tiles:
+        monkeypatch.setenv("TOYGPU_NO_TILES", "1")
+    r = _ref(wl)
+    r.load(wl.pos)
+    after = []
+
+    def cb(it):
+        s = r.read()
+        if it > 0:
+            s["hw"], s["delta"] = r.wvt_scratch()
+            after.append(s)
+        return 0
+
+    niter = 3
+    r.regularise(niter + 1, cb)
+    log = ref.parse_log(r.log())
+    g = tc.HotPath.from_workload(wl, flags=tc.WVT_SEQUENTIAL)
+    g.upload(wl.pos)
+    for it in range(niter):
+        g.wvt_iteration(log[it + 1]["step"])
+        s, o = after[it], g.download()
+        hw, dl = g.wvt_scratch()
+        assert np.array_equal(o["id"], s["id"]), it
+        for k in ("rho_model", "hsml", "rho", "varhsml", "pos"):
+            assert np.array_equal(o[k], s[k]), (it, k, (o[k] != s[k]).mean())
+        assert np.array_equal(hw, s["hw"]), it
+        assert np.array_equal(dl, s["delta"]), it
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_gpu_default_mode_and_rotA_with_displaced_nodes(wl):
+    """Default (tile + tree-sum) mode: rho/hsml bit-exact, displacement within 1e-5; rot(A)
+    over the pruned neighbour sets within 1e-5 of the reference."""
+    r = _ref(wl)
+    r.load(wl.pos)
+    r.find_sph_quantities()
+    d0 = r.read()
+    g = tc.HotPath.from_workload(wl)
+    g.upload(wl.pos)
+    g.find_sph_quantities()
+    o = g.download()
+    for k in ("hsml", "rho", "varhsml"):
+        assert np.array_equal(o[k], d0[k]), k
+    # warm pass from the reference's state: tile path with hand-backs
+    r.find_sph_quantities()
+    d1 = r.read()
+    g.find_sph_quantities()
+    o = g.download()
+    assert g.stats()["handed_back"] > 0
+    for k in ("hsml", "rho", "varhsml"):
+        assert np.array_equal(o[k], d1[k]), k
+    rng = np.random.default_rng(5)
+    apot = rng.standard_normal((N, 3)).astype(np.float32)
+    assert np.array_equal(o["id"], d1["id"])
+    r.set_apot(apot)                        # current (Peano) order on both sides
+    r.bfld_from_rotA()
+    want = r.read()["bfld"]
+    g.set_apot(apot)
+    g.bfld_from_rotA_sph()
+    got = g.download(bfld=True)["bfld"]
+    scale = np.abs(want).max(axis=1, keepdims=True) + 1e-30
+    assert (np.abs(got - want) / scale).max() < 1e-5

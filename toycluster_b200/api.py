@@ -28,6 +28,7 @@ NGBMAX = 2360      # globals.h:50
 NUMITER = 64       # wvt_relax.c:7
 
 WVT_SEQUENTIAL = 1  # tg_config.flags
+EXACT_NEIGHBOURS = 2  # tg_config.flags: exact predicate sets, not the reference tree's (include/toygpu.h)
 
 
 class ToyGpuError(RuntimeError):
@@ -50,7 +51,8 @@ class Stats(C.Structure):
     _fields_ = [("pair_evals", C.c_ulonglong), ("gathered", C.c_ulonglong),
                 ("searches", C.c_ulonglong), ("hsml_iters", C.c_ulonglong),
                 ("kernels", C.c_ulonglong), ("sweep_ms", C.c_double), ("step_ms", C.c_double),
-                ("handed_back", C.c_ulonglong)]
+                ("handed_back", C.c_ulonglong), ("displaced_nodes", C.c_ulonglong),
+                ("displaced_particles", C.c_ulonglong), ("displaced_overflow", C.c_ulonglong)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

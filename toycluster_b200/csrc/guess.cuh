@@ -40,15 +40,12 @@ __global__ void k_cpl(int n, const uint64_t *__restrict__ hi, const uint64_t *__
                     : (signed char)common_triplets(hi[b - 1], lo[b - 1], hi[b], lo[b]);
 }
 
-// Collapse decided when particle b is inserted: ev_start[b] = first particle of the new
-// leaf (or -1), ev_level[b], ev_count[b].
-__global__ void k_collapse_events(int n, const signed char *__restrict__ cpl,
-                                  int *__restrict__ ev_start, signed char *__restrict__ ev_level,
-                                  signed char *__restrict__ ev_count)
+// Collapse decided when particle b is inserted: start = first particle of the new leaf (or
+// -1), its level and particle count.
+static __device__ __forceinline__ void collapse_event(int b, const signed char *__restrict__ cpl,
+                                                      int &start, int &level, int &count)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n) return;
-    int start = -1, level = 0, count = 0;
+    start = -1; level = 0; count = 0;
     if (b >= 2 && cpl[b] < cpl[b - 1]) {
         // particles b-1, b-2, ... sharing at least `lvl` triplets with b-1
         auto run = [&](int lvl) {
@@ -64,6 +61,16 @@ __global__ void k_collapse_events(int n, const signed char *__restrict__ cpl,
             if (cl <= 8) { start = b - cl; level = ll; count = cl; }
         }
     }
+}
+
+__global__ void k_collapse_events(int n, const signed char *__restrict__ cpl,
+                                  int *__restrict__ ev_start, signed char *__restrict__ ev_level,
+                                  signed char *__restrict__ ev_count)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    int start, level, count;
+    collapse_event(b, cpl, start, level, count);
     ev_start[b] = start;
     ev_level[b] = (signed char)level;
     ev_count[b] = (signed char)count;

@@ -84,7 +84,7 @@ static __device__ __forceinline__ float box_box_dist2(float ax, float ay, float 
 static __device__ __forceinline__ float tile_radius(float hA, float hw_raw, float norm, double box)
 {
     const float hB = (float)((double)hA * 1.23);                   // sph.c:51
-    const float hsw = (float)((double)__fmul_rn(hw_raw, norm) * box);   // wvt_relax.c:124,135
+    const float hsw = (float)((double)__fmul_rn(fabsf(hw_raw), norm) * box);   // wvt_relax.c:124,135
     return fmaxf(hB, hsw);
 }
 
@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
             // (2) classify every hit, build the separation list, sum the displacement
             int cntA = 0, cntB = 0, cntW = 0;      // cntA, cntW: per-lane until reduced below
             bool ranges_ok = true;                 // every separation fit for the hoisted divide
+            bool displaced = false;                // a hit underneath a displaced reference node
             float sx = 0, sy = 0, sz = 0;
             const float Af = (float)A;
             for (int base = 0; base < nU; base += 32) {
@@ -372,6 +373,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 }
                 const float r2 = sq3_nofma(dx, dy, dz);                          // tree.c:88
                 const bool inA = live && r2 < hA2, inB = live && r2 < hB2, inW = live && r2 < hsw2;
+                displaced |= (inB | inW) & df_flagged(pj.w);
                 const unsigned mB = __ballot_sync(FULL_MASK, inB);
                 if (MODE & MODE_DENSITY) {
                     if (inB) {
@@ -405,6 +407,8 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
             }
             ranges_ok = __all_sync(FULL_MASK, ranges_ok);
             __syncwarp();
+            // the open tests of defect.cuh depend on the search radius: generic path
+            if (__any_sync(FULL_MASK, displaced)) { hand_back(i); continue; }
 
             float h = hA, rho = 0, drho = 0;
             bool ok = true;

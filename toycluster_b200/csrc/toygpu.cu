@@ -79,6 +79,9 @@ struct tg_ctx {
     int *ev_start = nullptr;
     float *guess = nullptr;
 
+    // displaced reference-tree nodes (defect.cuh)
+    DefectTab defect{};
+
     // scalars / scratch
     Halo *halos = nullptr;
     int nhalos = 0;
@@ -148,7 +151,8 @@ extern "C" int tg_destroy(tg_ctx *c)
                     c->hist, c->pw, c->hsml_in, c->rho_model, c->rm_state, c->rm_state_s, c->id_s, c->key_lo_s, c->apot_s,
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->sub_mem, c->cpl,
                     c->ev_level, c->ev_count, c->ev_start, c->guess, c->halos, c->partial, c->scal,
-                    c->flags, c->counters, c->gscratch, c->tile_ng, c->tile_groups, c->worklist};
+                    c->flags, c->counters, c->gscratch, c->tile_ng, c->tile_groups, c->worklist,
+                    c->defect.events, c->defect.counts, c->defect.nodes, c->defect.dmap};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
@@ -270,6 +274,13 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     CUC(dmalloc(&c->ev_count, n));
     CUC(dmalloc(&c->ev_start, n));
     CUC(dmalloc(&c->guess, n));
+    c->defect.cap_events = 4096;
+    c->defect.cap_nodes = std::max(1 << 20, n / 2);
+    CUC(dmalloc(&c->defect.events, c->defect.cap_events));
+    CUC(dmalloc(&c->defect.counts, 4));
+    CUC(dmalloc(&c->defect.nodes, c->defect.cap_nodes));
+    CUC(dmalloc(&c->defect.dmap, n));
+    CUC(cudaMemsetAsync(c->defect.counts, 0, 4 * sizeof(int), c->stream));
 
     CUC(dmalloc(&c->halos, MAX_HALOS));
     c->npartial = cdiv(n, RED_THREADS);
@@ -541,9 +552,20 @@ static int prepare_index(tg_ctx *c)
         LAUNCH_CHECK();
     }
 
-    if (c->any_cold) {   // tree.c:113-121 stand-in for particles with Hsml == 0
+    const bool emulate = !(c->cfg.flags & TG_EXACT_NEIGHBOURS);
+    if (c->any_cold || emulate) {
         k_cpl<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->key_lo_s, c->cpl);
         LAUNCH_CHECK();
+    }
+    CU(cudaMemsetAsync(c->defect.counts, 0, 4 * sizeof(int), c->stream));
+    if (emulate) {       // tree.c:298-310: nodes displaced by the sign test, and what they prune
+        k_defect_detect<<<cdiv(n, T), T, 0, c->stream>>>(n, c->pw, c->box.box_d, c->cpl, c->defect);
+        LAUNCH_CHECK();
+        k_defect_paths<<<64, 128, 0, c->stream>>>(n, c->pw, c->box.box_d, c->key_hi_s, c->key_lo_s,
+                                                 c->cpl, c->defect);
+        LAUNCH_CHECK();
+    }
+    if (c->any_cold) {   // tree.c:113-121 stand-in for particles with Hsml == 0
         k_collapse_events<<<cdiv(n, T), T, 0, c->stream>>>(n, c->cpl, c->ev_start, c->ev_level, c->ev_count);
         LAUNCH_CHECK();
         k_guess_hsml<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->key_lo_s, c->cpl, c->ev_start,
@@ -589,6 +611,8 @@ static SweepArgs sweep_args(tg_ctx *c, double step)
     a.nwork = c->flags + 5;
     a.tile_ng = c->tile_ng;
     a.tile_groups = c->tile_groups;
+    a.dmap = c->defect.dmap;
+    a.dnodes = c->defect.nodes;
     return a;
 }
 
@@ -634,9 +658,13 @@ template <int MODE> static int launch_sweep(tg_ctx *c, const SweepArgs &a)
 
 static int check_flags(tg_ctx *c)
 {
-    int f[4];
+    int f[4], dc[4];
     CU(cudaMemcpyAsync(f, c->flags, sizeof f, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(dc, c->defect.counts, sizeof dc, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    c->stats.displaced_nodes = dc[0];
+    c->stats.displaced_particles = dc[3];
+    c->stats.displaced_overflow = dc[2];
     if (f[2]) return fail(c, TG_ERANGE, "particle position outside [0, Boxsize] (peano.c:130-132)");
     if (f[1]) return fail(c, TG_ENOCONV, "hsml iteration did not terminate (fewer than %d gas particles in reach?)", TG_DESNNGB);
     return TG_OK;
@@ -701,6 +729,7 @@ static int finish_stats(tg_ctx *c, bool have_sweep_events)
     CU(cudaMemcpyAsync(&nwork, c->flags + 5, sizeof nwork, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->stats.handed_back = (unsigned long long)nwork;
+
     c->stats.pair_evals = h[0];
     c->stats.gathered = h[1];
     c->stats.searches = h[2];
@@ -942,7 +971,7 @@ extern "C" int tg_wvt_scratch(tg_ctx *c, float *hsml_wvt, float *delta)
         CU(cudaMemcpy(h.data(), c->pw, sizeof(float4) * n, cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(&vsum, c->scal, sizeof(double), cudaMemcpyDeviceToHost));
         const float norm = (float)pow(TG_DESNNGB / vsum / K_FOURPITHIRD, 1.0 / 3.0);   // wvt_relax.c:120
-        for (int i = 0; i < n; i++) hsml_wvt[i] = h[i].w * norm;
+        for (int i = 0; i < n; i++) hsml_wvt[i] = fabsf(h[i].w) * norm;   // sign bit: defect.cuh flag
     }
     if (delta) {
         std::vector<float> d((size_t)3 * n);
@@ -991,7 +1020,7 @@ extern "C" int tg_find_ngb(tg_ctx *c, int i, float h, int32_t *list, int *count)
     CU(cudaSetDevice(c->cfg.device));
     int *d = nullptr;
     CU(dmalloc(&d, TG_NGBMAX + 1));
-    k_find_ngb<<<1, 32, 0, c->stream>>>(c->bvh, c->box, c->pw, i, h, d, d + TG_NGBMAX);
+    k_find_ngb<<<1, 32, 0, c->stream>>>(c->bvh, c->box, c->pw, i, h, c->defect.dmap, c->defect.nodes, d, d + TG_NGBMAX);
     c->launches++;
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = cudaMemcpy(count, d + TG_NGBMAX, sizeof(int), cudaMemcpyDeviceToHost);

@@ -257,3 +257,23 @@ def make(name: str, n_gas: int | None = None, seed: int = 14041981,
     if with_positions:
         w.pos = sample_positions(w, seed)
     return w
+
+
+def snap_to_cell_planes(pos: np.ndarray, boxsize: float, count: int, seed: int = 7,
+                        levels=(3, 4, 5, 6, 7)) -> np.ndarray:
+    """Stress input for the reference octree's node placement (tree.c:298-310): move one
+    coordinate of ``count`` particles exactly onto the centre plane of the level-(L-1) cell
+    they lie in.  Such a particle belongs to the upper level-L cell by its key, while the sign
+    test ``Pos > centre`` says lower, so whenever it is the first particle of its cell the
+    reference displaces that node and its whole subtree by one cell size.  Production inputs
+    do this by chance (~8 nodes per 1e6 particles); this makes it common at test sizes."""
+    rng = np.random.default_rng(seed)
+    out = np.array(pos, dtype=np.float32, copy=True)
+    pick = rng.choice(len(out), size=count, replace=False)
+    for i in pick:
+        L = int(rng.choice(levels))
+        d = int(rng.integers(3))
+        cells = 1 << (L - 1)
+        k = min(int(np.float64(out[i, d]) / boxsize * cells), cells - 1)
+        out[i, d] = np.float32(boxsize * (k + 0.5) / cells)
+    return out
