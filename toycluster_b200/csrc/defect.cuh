@@ -40,7 +40,9 @@
 
 struct DefectTab {
     int2 *events;        // (first particle, level)
-    int *counts;         // [0] events, [1] path nodes used, [2] overflow, [3] flagged particles
+    int2 *big;           // [DF_BIG_CAP] (first, end) of cells too large for one block
+    int *counts;         // [0] events, [1] path nodes used, [2] overflow, [3] flagged particles,
+                         // [4] big cells
     float4 *nodes;       // (centre, size) per path level, terminated by size == 0
     int *dmap;           // [n] path offset of a flagged particle
     int cap_events, cap_nodes;
@@ -108,6 +110,45 @@ static __device__ int df_leaf_level(int p, int n, const signed char *__restrict_
     return level + 1;
 }
 
+// Literal path of particle k (levels 1 .. leaf level), flag and map entry.
+static __device__ void df_emit_path(int k, int n, float4 *__restrict__ pw, double box,
+                                    const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo,
+                                    const signed char *__restrict__ cpl, const DefectTab &d)
+{
+    const int L = min(df_leaf_level(k, n, cpl), DF_MAX_LEVEL);
+    const int off = atomicAdd(&d.counts[1], L + 1);
+    if (off + L + 1 > d.cap_nodes) { d.counts[2] = 1; return; }
+    const uint64_t kh = hi[k], kl = lo[k];
+    float cx = (float)(box / 2), cy = cx, cz = cx;
+    int f = 0;
+    for (int q = 1; q <= L; q++) {
+        uint64_t mh, ml;
+        df_mask(q, mh, ml);
+        const uint64_t ph = kh & mh, pl = kl & ml;          // smallest key of the cell
+        int a = f, z = k;                                   // first particle of the cell
+        while (a < z) {
+            const int mid = (a + z) >> 1;
+            if (key_less(hi[mid], lo[mid], ph, pl)) a = mid + 1; else z = mid;
+        }
+        f = a;
+        const float4 pf = pw[f];
+        const float s = df_size(box, q);
+        cx = df_child(cx, pf.x > cx, s);                    // tree.c:298-310
+        cy = df_child(cy, pf.y > cy, s);
+        cz = df_child(cz, pf.z > cz, s);
+        d.nodes[off + q - 1] = make_float4(cx, cy, cz, s);
+    }
+    d.nodes[off + L] = make_float4(0, 0, 0, 0);
+    d.dmap[k] = off;
+    float *w = &pw[k].w;
+    *w = __int_as_float(__float_as_int(*w) | 0x80000000);
+    atomicAdd(&d.counts[3], 1);
+}
+
+#define DF_BIG 8192          // cells above this size are shared by the whole grid (second kernel)
+#define DF_BIG_CAP 64
+
+// One block per event.  Cells larger than DF_BIG are only recorded in d.big.
 __global__ void k_defect_paths(int n, float4 *__restrict__ pw, double box,
                                const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo,
                                const signed char *__restrict__ cpl, DefectTab d)
@@ -115,7 +156,7 @@ __global__ void k_defect_paths(int n, float4 *__restrict__ pw, double box,
     __shared__ int s_first, s_end;
     const int nev = min(d.counts[0], d.cap_events);
     if (blockIdx.x == 0 && threadIdx.x == 0 && d.counts[0] > d.cap_events) d.counts[2] = 1;
-    for (int e = 0; e < nev; e++) {
+    for (int e = blockIdx.x; e < nev; e += gridDim.x) {
         __syncthreads();
         if (threadIdx.x == 0) {
             const int2 ev = d.events[e];
@@ -132,42 +173,30 @@ __global__ void k_defect_paths(int n, float4 *__restrict__ pw, double box,
                     if (!key_less(uh, ul, hi[mid], lo[mid])) a = mid + 1; else z = mid;
                 }
                 end = a;
+                if (end - i > DF_BIG) {
+                    const int b = atomicAdd(&d.counts[4], 1);
+                    if (b < DF_BIG_CAP) d.big[b] = make_int2(i, end); else d.counts[2] = 1;
+                    end = i;
+                }
             }
             s_first = i; s_end = end;
         }
         __syncthreads();
         const int first = s_first, end = s_end;
-        for (int k = first + blockIdx.x * blockDim.x + threadIdx.x; k < end;
-             k += gridDim.x * blockDim.x) {
-            const int L = min(df_leaf_level(k, n, cpl), DF_MAX_LEVEL);
-            const int off = atomicAdd(&d.counts[1], L + 1);
-            if (off + L + 1 > d.cap_nodes) { d.counts[2] = 1; continue; }
-            const uint64_t kh = hi[k], kl = lo[k];
-            float cx = (float)(box / 2), cy = cx, cz = cx;
-            int f = 0;
-            for (int q = 1; q <= L; q++) {
-                uint64_t mh, ml;
-                df_mask(q, mh, ml);
-                const uint64_t ph = kh & mh, pl = kl & ml;          // smallest key of the cell
-                int a = f, z = k;                                   // first particle of the cell
-                while (a < z) {
-                    const int mid = (a + z) >> 1;
-                    if (key_less(hi[mid], lo[mid], ph, pl)) a = mid + 1; else z = mid;
-                }
-                f = a;
-                const float4 pf = pw[f];
-                const float s = df_size(box, q);
-                cx = df_child(cx, pf.x > cx, s);                    // tree.c:298-310
-                cy = df_child(cy, pf.y > cy, s);
-                cz = df_child(cz, pf.z > cz, s);
-                d.nodes[off + q - 1] = make_float4(cx, cy, cz, s);
-            }
-            d.nodes[off + L] = make_float4(0, 0, 0, 0);
-            d.dmap[k] = off;
-            float *w = &pw[k].w;
-            *w = __int_as_float(__float_as_int(*w) | 0x80000000);
-            atomicAdd(&d.counts[3], 1);
-        }
+        for (int k = first + threadIdx.x; k < end; k += blockDim.x)
+            df_emit_path(k, n, pw, box, hi, lo, cpl, d);
+    }
+}
+
+__global__ void k_defect_paths_big(int n, float4 *__restrict__ pw, double box,
+                                   const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo,
+                                   const signed char *__restrict__ cpl, DefectTab d)
+{
+    const int nbig = min(d.counts[4], DF_BIG_CAP);
+    for (int b = 0; b < nbig; b++) {
+        const int2 r = d.big[b];
+        for (int k = r.x + blockIdx.x * blockDim.x + threadIdx.x; k < r.y; k += gridDim.x * blockDim.x)
+            df_emit_path(k, n, pw, box, hi, lo, cpl, d);
     }
 }
 

@@ -152,7 +152,7 @@ extern "C" int tg_destroy(tg_ctx *c)
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->sub_mem, c->cpl,
                     c->ev_level, c->ev_count, c->ev_start, c->guess, c->halos, c->partial, c->scal,
                     c->flags, c->counters, c->gscratch, c->tile_ng, c->tile_groups, c->worklist,
-                    c->defect.events, c->defect.counts, c->defect.nodes, c->defect.dmap};
+                    c->defect.events, c->defect.big, c->defect.counts, c->defect.nodes, c->defect.dmap};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
@@ -277,10 +277,11 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     c->defect.cap_events = 4096;
     c->defect.cap_nodes = std::max(1 << 20, n / 2);
     CUC(dmalloc(&c->defect.events, c->defect.cap_events));
-    CUC(dmalloc(&c->defect.counts, 4));
+    CUC(dmalloc(&c->defect.counts, 8));
+    CUC(dmalloc(&c->defect.big, DF_BIG_CAP));
     CUC(dmalloc(&c->defect.nodes, c->defect.cap_nodes));
     CUC(dmalloc(&c->defect.dmap, n));
-    CUC(cudaMemsetAsync(c->defect.counts, 0, 4 * sizeof(int), c->stream));
+    CUC(cudaMemsetAsync(c->defect.counts, 0, 8 * sizeof(int), c->stream));
 
     CUC(dmalloc(&c->halos, MAX_HALOS));
     c->npartial = cdiv(n, RED_THREADS);
@@ -557,12 +558,15 @@ static int prepare_index(tg_ctx *c)
         k_cpl<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->key_lo_s, c->cpl);
         LAUNCH_CHECK();
     }
-    CU(cudaMemsetAsync(c->defect.counts, 0, 4 * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->defect.counts, 0, 8 * sizeof(int), c->stream));
     if (emulate) {       // tree.c:298-310: nodes displaced by the sign test, and what they prune
         k_defect_detect<<<cdiv(n, T), T, 0, c->stream>>>(n, c->pw, c->box.box_d, c->cpl, c->defect);
         LAUNCH_CHECK();
-        k_defect_paths<<<64, 128, 0, c->stream>>>(n, c->pw, c->box.box_d, c->key_hi_s, c->key_lo_s,
-                                                 c->cpl, c->defect);
+        k_defect_paths<<<296, 128, 0, c->stream>>>(n, c->pw, c->box.box_d, c->key_hi_s, c->key_lo_s,
+                                                  c->cpl, c->defect);
+        LAUNCH_CHECK();
+        k_defect_paths_big<<<296, 128, 0, c->stream>>>(n, c->pw, c->box.box_d, c->key_hi_s,
+                                                      c->key_lo_s, c->cpl, c->defect);
         LAUNCH_CHECK();
     }
     if (c->any_cold) {   // tree.c:113-121 stand-in for particles with Hsml == 0
