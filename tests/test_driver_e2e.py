@@ -1,0 +1,97 @@
+"""the WHOLE reference program -- main.c, cluster.par parser, set-up, sampling,
+WVT relaxation, magnetic field, temperatures, velocities, Gadget writer, all unmodified
+reference sources -- built twice by oracle/Makefile (`make driver`): with its own
+tree.o/sph.o/wvt_relax.o/peano.o, and with toycluster_b200/host/gpu_shim.c + libtoygpu.so in
+their place.  Same parameter file in, Gadget IC file out; the files must agree block by block.
+(GSL is absent here; both variants link the same stand-in, oracle/compat/gsl_compat.c.)"""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFDIR = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
+CPU, GPU = os.path.join(REFDIR, "Toycluster_cpu"), os.path.join(REFDIR, "Toycluster_gpu")
+
+PAR = """Output_file ./{out}
+Ntotal      {ntotal}
+Mtotal      1e5
+Mass_Ratio  {mass_ratio}
+ImpactParam 50
+ZeroEOrbitFrac 0.8
+Cuspy       0
+Redshift	0.87
+Bfld_Norm   20e-6
+Bfld_Eta    0.5
+Bfld_Scale  100
+bf          0.17
+h_100       0.7
+UnitLength_in_cm 			3.085678e21
+UnitMass_in_g 				1.989e43
+UnitVelocity_in_cm_per_s 	1e5
+"""
+
+
+def read_gadget2(path):
+    """Format-2 snapshot as io.c:41-133 writes it -> {label: raw bytes}."""
+    blocks = {}
+    with open(path, "rb") as f:
+        data = f.read()
+    off = 0
+    while off < len(data):
+        (sz,) = struct.unpack_from("<i", data, off)
+        assert sz == 8
+        label = data[off + 4:off + 8].decode()
+        off += 4 + 8 + 4
+        (n,) = struct.unpack_from("<i", data, off)
+        blocks[label] = data[off + 4:off + 4 + n]
+        off += 4 + n + 4
+    return blocks
+
+
+def run(exe, par, cwd, env_extra):
+    env = dict(os.environ, OMP_NUM_THREADS="1", **env_extra)
+    r = subprocess.run([exe, par], cwd=cwd, env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+needs_drivers = pytest.mark.skipif(not (os.path.exists(CPU) and os.path.exists(GPU)),
+                                   reason="oracle/_ref drivers not built (make -C oracle driver)")
+
+
+@needs_drivers
+def test_cpu_driver_runs_and_writes_all_blocks(tmp_path):
+    (tmp_path / "a.par").write_text(PAR.format(out="IC_a", ntotal=6000, mass_ratio=0))
+    out = run(CPU, "a.par", tmp_path, {})
+    assert "Starting iterative SPH regularisation" in out and "#00: Err max=" in out
+    b = read_gadget2(tmp_path / "IC_a")
+    assert [k.strip() for k in b] == ["HEAD", "POS", "VEL", "ID", "U", "RHO", "HSML", "BFLD", "RHOM"]
+    assert len(b["POS "]) == 6000 * 12 and len(b["RHO "]) == 3000 * 4
+
+
+@pytest.mark.gpu
+@needs_drivers
+@pytest.mark.parametrize("mass_ratio,ntotal", [(0, 20000), (0.3125, 24000)])
+def test_gpu_driver_writes_the_same_gadget_file(tmp_path, mass_ratio, ntotal):
+    (tmp_path / "c.par").write_text(PAR.format(out="IC_c", ntotal=ntotal, mass_ratio=mass_ratio))
+    (tmp_path / "g.par").write_text(PAR.format(out="IC_g", ntotal=ntotal, mass_ratio=mass_ratio))
+    out_c = run(CPU, "c.par", tmp_path, {})
+    out_g = run(GPU, "g.par", tmp_path, {"TOYGPU_FLAGS": "1"})      # TG_WVT_SEQUENTIAL
+    # the per-iteration log lines of wvt_relax.c:91-92, as printed
+    it_c = [l for l in out_c.splitlines() if l.lstrip().startswith("#")]
+    it_g = [l for l in out_g.splitlines() if l.lstrip().startswith("#")]
+    assert len(it_c) >= 3 and it_c == it_g
+    c, g = read_gadget2(tmp_path / "IC_c"), read_gadget2(tmp_path / "IC_g")
+    assert list(c) == list(g)
+    for label in c:
+        if label == "BFLD":
+            continue
+        assert c[label] == g[label], label
+    # rot(A) sums in FP64 trees instead of serially: 1e-5 of the field scale
+    bc = np.frombuffer(c["BFLD"], np.float32).reshape(-1, 3)
+    bg = np.frombuffer(g["BFLD"], np.float32).reshape(-1, 3)
+    scale = np.abs(bc).max(axis=1, keepdims=True) + 1e-30
+    assert (np.abs(bg - bc) / scale).max() < 1e-5

@@ -48,6 +48,8 @@ static void ensure_context(void)
     cfg.mpart_gas = Param.Mpart[0];
     cfg.mtotal = Param.Mtotal;
     cfg.flags = Shim_flags;
+    if (getenv("TOYGPU_FLAGS"))      /* e.g. 1 = TG_WVT_SEQUENTIAL, 2 = TG_EXACT_NEIGHBOURS */
+        cfg.flags |= (unsigned)strtoul(getenv("TOYGPU_FLAGS"), NULL, 0);
     cfg.rank = 0;
     cfg.nranks = 1;
 
