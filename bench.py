@@ -265,6 +265,14 @@ def main():
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    per_rank = torch.tensor([acc["sweep_ms"] / args.steps, acc["step_ms"] / args.steps],
+                            dtype=torch.float64, device="cuda")
+    if world > 1:
+        allr = [torch.empty_like(per_rank) for _ in range(world)]
+        dist.all_gather(allr, per_rank)
+        per_rank = torch.stack(allr)
+    else:
+        per_rank = per_rank[None]
     ms_total, wall_ms, sweep_ms_max = red.tolist()
     pair_evals, gathered = tot.tolist()
 
@@ -350,6 +358,9 @@ def main():
             "gathered_per_particle": gathered / args.steps / n,
             "wall_ms_per_step": wall_ms / args.steps,
             "gpu_launches": int(acc["kernels"]), "clocks": clocks, "roofline": roofline}
+    if world > 1:     # per-rank device times: load balance of the target partition
+        line["per_rank_ms"] = {"sweep": [round(v, 3) for v in per_rank[:, 0].tolist()],
+                               "step": [round(v, 3) for v in per_rank[:, 1].tolist()]}
     if e2e:
         line["e2e"] = e2e
     if full:

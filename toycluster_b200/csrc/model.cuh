@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(RED_THREADS)
 k_reorder_model(int n, const int *__restrict__ idx, const float4 *__restrict__ posh_in,
                 const int *__restrict__ id_in, const uint64_t *__restrict__ key_lo_in,
                 const float *__restrict__ apot_in, const float *__restrict__ rmstate_in,
-                float *__restrict__ rmstate_out, float4 *__restrict__ pw, float *__restrict__ hsml, int *__restrict__ id_out,
+                float *__restrict__ rmstate_out, float4 *__restrict__ pw, float *__restrict__ soa,
+                float *__restrict__ hsml, int *__restrict__ id_out,
                 float *__restrict__ rho_model, uint64_t *__restrict__ key_lo_out,
                 float *__restrict__ apot_out,
                 const Halo *__restrict__ halos, int nhalos, double mpart, double boxhalf,
@@ -124,6 +125,8 @@ k_reorder_model(int n, const int *__restrict__ idx, const float4 *__restrict__ p
         // wvt_relax.c:115: hsml = pow(WVTNNGB * Mpart / rho / fourpithird, 1/3) -> float
         const float hw = (float)pow(TG_DESNNGB * mpart / (double)rm / K_FOURPITHIRD, 1. / 3.);
         pw[k] = make_float4(p.x, p.y, p.z, hw);
+        const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
+        soa[k] = p.x; soa[n8 + k] = p.y; soa[2 * n8 + k] = p.z;
         hsml[k] = p.w;
         id_out[k] = id_in[src];
         rho_model[k] = rm;
@@ -135,6 +138,10 @@ k_reorder_model(int n, const int *__restrict__ idx, const float4 *__restrict__ p
             apot_out[3 * k + 2] = apot_in[3 * src + 2];
         }
         cube = (double)__fmul_rn(__fmul_rn(hw, hw), hw);   // p3() on the float, wvt_relax.c:117
+    }
+    else if (k < (int)(((size_t)n + 7) & ~(size_t)7)) {      // pad: never within reach of anything
+        const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
+        soa[k] = 1e18f; soa[n8 + k] = 1e18f; soa[2 * n8 + k] = 1e18f;
     }
     const double s = block_sum(cube, sm);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;

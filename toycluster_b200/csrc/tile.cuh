@@ -38,6 +38,7 @@
 #include "common.cuh"
 #include "bvh.cuh"
 #include "sph.cuh"
+#include "f32x2.cuh"
 
 #define TL_WARPS 8
 #ifndef TL_ENT
@@ -164,6 +165,59 @@ __global__ void k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw,
     }
 }
 
+// Phase 1 of the tile sweep: lane = target, one bit per (target, candidate).
+// The bit only has to be a SUPERSET of the exact predicate (phase 2 re-evaluates every hit
+// with the FMA-free arithmetic of tree.c:88), so the sum of squares is contracted to two FMAs
+// and compared against a radius inflated by 2e-6.  Two candidates per instruction: the SoA
+// copy of the positions delivers aligned pairs, and FADD2/FMUL2/FFMA2 (f32x2.cuh) work on both
+// at once (the target's coordinate is the scalar operand).  The periodic wrap is
+// d - Boxsize * rint(d / Boxsize) by the 1.5*2^23 trick, which differs from the reference's
+// only for |d| within 1e-7 of Boxsize/2 -- where it changes d^2 by less than the inflation.
+template <bool INTERIOR>
+static __device__ __forceinline__ void tile_phase1(const float *__restrict__ sx, const float *__restrict__ sy,
+                                                   const float *__restrict__ sz, const int *s_run,
+                                                   unsigned *s_mask, int w, int lane, int ng, int nruns,
+                                                   float xi, float yi, float zi, float R2, float box)
+{
+    const float R2p = R2 * 1.000002f;
+    const f32x2 xi2 = pack2(xi, xi), yi2 = pack2(yi, yi), zi2 = pack2(zi, zi);
+    const float ibox = 1.f / box;
+    const f32x2 ib2 = pack2(ibox, ibox), mg2 = pack2(12582912.f, 12582912.f);
+    const f32x2 nb2 = pack2(-box, -box);
+    for (int q = w; q < ng; q += TL_WARPS) {
+        unsigned word = 0;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {            // four runs of 8 candidates per word
+            const int r8 = 4 * q + c;
+            if (r8 >= nruns) break;
+            const int first = s_run[r8];         // multiple of 8: 32-byte aligned rows
+            // same address in every lane: broadcast loads, six in flight
+            const ulonglong2 x0 = __ldg((const ulonglong2 *)(sx + first)), x1 = __ldg((const ulonglong2 *)(sx + first) + 1);
+            const ulonglong2 y0 = __ldg((const ulonglong2 *)(sy + first)), y1 = __ldg((const ulonglong2 *)(sy + first) + 1);
+            const ulonglong2 z0 = __ldg((const ulonglong2 *)(sz + first)), z1 = __ldg((const ulonglong2 *)(sz + first) + 1);
+            unsigned sub = 0;
+            auto test2 = [&](f32x2 X, f32x2 Y, f32x2 Z, unsigned b0, unsigned b1) {
+                f32x2 dx = sub2(xi2, X), dy = sub2(yi2, Y), dz = sub2(zi2, Z);
+                if (!INTERIOR) {
+                    dx = fma2(sub2(fma2(dx, ib2, mg2), mg2), nb2, dx);
+                    dy = fma2(sub2(fma2(dy, ib2, mg2), mg2), nb2, dy);
+                    dz = fma2(sub2(fma2(dz, ib2, mg2), mg2), nb2, dz);
+                }
+                float s0, s1;
+                unpack2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), s0, s1);
+                if (s0 < R2p) sub |= b0;
+                if (s1 < R2p) sub |= b1;
+            };
+            test2(x0.x, y0.x, z0.x, 1u, 2u);
+            test2(x0.y, y0.y, z0.y, 4u, 8u);
+            test2(x1.x, y1.x, z1.x, 16u, 32u);
+            test2(x1.y, y1.y, z1.y, 64u, 128u);
+            word |= sub << (8 * c);              // the pad of a short last run is far away
+        }
+        s_mask[q * TL_MSTRIDE + lane] = word;
+    }
+}
+
 struct TileList {     // density list: r as double; the sign bit marks "outside the Hsml list"
     double *sm;
     __device__ __forceinline__ double get(int k) const { return fabs(sm[k]); }
@@ -252,41 +306,9 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 const float R = tile_radius(a.hsml_in[i], pi.w, norm, a.bx.box_d);
                 R2 = __fmul_rn(R, R);
             }
-            // The bit only has to be a SUPERSET of the exact predicate (phase 2 re-evaluates
-            // every hit with the FMA-free arithmetic of tree.c:88), so the sum of squares is
-            // contracted to two FMAs and compared against a radius inflated by 1e-6.
-            const float R2p = R2 * 1.000001f;
-            auto test = [&](const float4 p) -> bool {
-                float dx = __fsub_rn(xi, p.x), dy = __fsub_rn(yi, p.y), dz = __fsub_rn(zi, p.z);
-                if (!interior) {
-                    dx = fabsf(dx); dy = fabsf(dy); dz = fabsf(dz);
-                    if (dx > boxhalf) dx = __fsub_rn(dx, box);
-                    if (dy > boxhalf) dy = __fsub_rn(dy, box);
-                    if (dz > boxhalf) dz = __fsub_rn(dz, box);
-                }
-                return fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < R2p;
-            };
-            for (int q = w; q < ng; q += TL_WARPS) {
-                unsigned word = 0;
-#pragma unroll 1
-                for (int c = 0; c < 4; c++) {            // four runs of 8 candidates per word
-                    const int r8 = 4 * q + c;
-                    if (r8 >= nruns) break;
-                    const int first = s_run[r8];
-                    const float4 *cand = a.pw + first;   // same address in every lane: broadcast
-                    unsigned sub = 0;
-                    if (first + 8 <= n) {
-#pragma unroll
-                        for (int b = 0; b < 8; b++)      // 8 independent loads in flight
-                            if (test(__ldg(cand + b))) sub |= 1u << b;
-                    } else {                             // the last run may be short
-                        for (int b = 0; b < n - first; b++)
-                            if (test(__ldg(cand + b))) sub |= 1u << b;
-                    }
-                    word |= sub << (8 * c);
-                }
-                s_mask[q * TL_MSTRIDE + lane] = word;
-            }
+            const size_t n8 = ((size_t)n + 7) & ~(size_t)7;      // stride of the SoA copy
+            if (interior) tile_phase1<true>(a.soa, a.soa + n8, a.soa + 2 * n8, s_run, s_mask, w, lane, ng, nruns, xi, yi, zi, R2, box);
+            else tile_phase1<false>(a.soa, a.soa + n8, a.soa + 2 * n8, s_run, s_mask, w, lane, ng, nruns, xi, yi, zi, R2, box);
         }
         __syncthreads();
 

@@ -60,6 +60,7 @@ struct tg_ctx {
 
     // sorted
     float4 *pw = nullptr;
+    float *soa = nullptr;           // x[n8], y[n8], z[n8] copy of pw for the tile sweep's phase 1
     float *hsml_in = nullptr, *rho_model = nullptr;
     float *rm_state = nullptr, *rm_state_s = nullptr;   // SphP.Rho_Model as the driver sees it (current order)
     int *id_s = nullptr;
@@ -148,7 +149,7 @@ extern "C" int tg_destroy(tg_ctx *c)
     if (!c) return TG_OK;
     cudaSetDevice(c->cfg.device);
     void *ptrs[] = {c->posh, c->id, c->apot, c->stage, c->key_hi, c->key_lo, c->key_tmp, c->idx, c->idx_tmp,
-                    c->hist, c->pw, c->hsml_in, c->rho_model, c->rm_state, c->rm_state_s, c->id_s, c->key_lo_s, c->apot_s,
+                    c->hist, c->pw, c->soa, c->hsml_in, c->rho_model, c->rm_state, c->rm_state_s, c->id_s, c->key_lo_s, c->apot_s,
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->sub_mem, c->cpl,
                     c->ev_level, c->ev_count, c->ev_start, c->guess, c->halos, c->partial, c->scal,
                     c->flags, c->counters, c->gscratch, c->tile_ng, c->tile_groups, c->worklist,
@@ -225,6 +226,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     c->ntiles = cdiv(n, RS_TILE);
     CUC(dmalloc(&c->hist, (size_t)RS_BINS * c->ntiles + RS_BINS));   // + digit totals
     CUC(dmalloc(&c->pw, n));
+    CUC(dmalloc(&c->soa, 3 * (((size_t)n + 7) & ~(size_t)7)));
     CUC(dmalloc(&c->hsml_in, n));
     CUC(dmalloc(&c->rho_model, n));
     CUC(dmalloc(&c->rm_state, n));
@@ -529,7 +531,7 @@ static int prepare_index(tg_ctx *c)
 
     k_reorder_model<<<c->npartial, RED_THREADS, 0, c->stream>>>(
         n, c->idx_s, c->posh, c->id, c->key_lo, c->have_apot ? c->apot : nullptr, c->rm_state,
-        c->rm_state_s, c->pw, c->hsml_in,
+        c->rm_state_s, c->pw, c->soa, c->hsml_in,
         c->id_s, c->rho_model, c->key_lo_s, c->apot_s, c->halos, c->nhalos, c->box.mpart,
         c->box.boxhalf_d, c->partial);
     LAUNCH_CHECK();
@@ -592,6 +594,7 @@ static SweepArgs sweep_args(tg_ctx *c, double step)
     a.t = c->bvh;
     a.bx = c->box;
     a.pw = c->pw;
+    a.soa = c->soa;
     a.hsml_in = c->hsml_in;
     a.guess = c->guess;
     a.hsml_out = c->hsml_out;
