@@ -94,6 +94,11 @@ typedef struct {
                                                 in the current index (superset count) */
     unsigned long long displaced_particles;  /* particles underneath them (carry a path) */
     unsigned long long displaced_overflow;   /* 1: path table full, some left unreproduced */
+    unsigned long long handback_why[5];      /* hand-backs of the step by reason: whole tile (cold
+                                                or too many candidate runs), hit list full,
+                                                displaced-node candidate in reach, a third
+                                                search or density list full, no convergence on
+                                                the frozen list */
 } tg_stats;
 
 /* ---- life cycle -------------------------------------------------------------------- */

@@ -149,12 +149,12 @@ def test_gpu_default_mode_and_rotA_with_displaced_nodes(wl):
     o = g.download()
     for k in ("hsml", "rho", "varhsml"):
         assert np.array_equal(o[k], d0[k]), k
-    # warm pass from the reference's state: tile path with hand-backs
+    # warm pass from the reference's state: tile path
     r.find_sph_quantities()
     d1 = r.read()
     g.find_sph_quantities()
     o = g.download()
-    assert g.stats()["handed_back"] > 0
+    assert g.stats()["displaced_particles"] > 50      # the tile sweep applies the open tests itself
     for k in ("hsml", "rho", "varhsml"):
         assert np.array_equal(o[k], d1[k]), k
     rng = np.random.default_rng(5)

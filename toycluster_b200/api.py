@@ -52,10 +52,12 @@ class Stats(C.Structure):
                 ("searches", C.c_ulonglong), ("hsml_iters", C.c_ulonglong),
                 ("kernels", C.c_ulonglong), ("sweep_ms", C.c_double), ("step_ms", C.c_double),
                 ("handed_back", C.c_ulonglong), ("displaced_nodes", C.c_ulonglong),
-                ("displaced_particles", C.c_ulonglong), ("displaced_overflow", C.c_ulonglong)]
+                ("displaced_particles", C.c_ulonglong), ("displaced_overflow", C.c_ulonglong),
+                ("handback_why", C.c_ulonglong * 5)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (list(getattr(self, k)) if k == "handback_why" else getattr(self, k))
+                for k, _ in self._fields_}
 
 
 class _Exchange(C.Structure):

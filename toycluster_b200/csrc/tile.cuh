@@ -244,16 +244,15 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
     const float binv_hi = (float)a.bx.boxinv_d, binv_lo = (float)(a.bx.boxinv_d - (double)binv_hi);
     const int n = a.t.n;
 
-    // lowest-set-bit index by de Bruijn multiplication + a 32-byte table: the expansion loop
-    // below would otherwise issue BREV+FLO on the XU pipe for every hit
-    unsigned char *s_bit = (unsigned char *)(s_misc + 4);
-    if (threadIdx.x < 32) s_bit[(0x077CB531u << threadIdx.x) >> 27] = (unsigned char)threadIdx.x;
 
     unsigned long long c_evals = 0, c_gath = 0, c_pairs = 0;
     unsigned c_search = 0, c_iters = 0;
 
-    auto hand_back = [&](int i) {     // redo target i on the generic path
-        if (lane == 0) a.worklist[atomicAdd(a.nwork, 1)] = i;
+    auto hand_back = [&](int i, int why) {     // redo target i on the generic path
+        if (lane == 0) {
+            a.worklist[atomicAdd(a.nwork, 1)] = i;
+            atomicAdd(&a.counters[4 + why], 1ull);
+        }
     };
 
     for (;;) {
@@ -266,7 +265,10 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
         if (code < 0) {               // whole tile to the generic path
             if (w == 0) {
                 const int i = tile * 32 + lane;
-                if (i < n) a.worklist[atomicAdd(a.nwork, 1)] = i;
+                if (i < n) {
+                    a.worklist[atomicAdd(a.nwork, 1)] = i;
+                    atomicAdd(&a.counters[4], 1ull);
+                }
             }
             continue;
         }
@@ -321,7 +323,8 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
             const int i = tile * 32 + tsel;
             if (i >= n) continue;
 
-            const float4 pi = a.pw[i];
+            float4 pi = a.pw[i];
+            pi.w = fabsf(pi.w);                    // the sign bit is the displaced-node flag
             const float hA = a.hsml_in[i];
             const float hB = (float)((double)hA * 1.23);                        // sph.c:51
             const float hi_w = __fmul_rn(pi.w, norm);                           // wvt_relax.c:124
@@ -331,12 +334,16 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
 
             // (1) expand the bit row into a compact candidate-slot list.  Every lane owns the
             //     words lane, lane+32, ... of the row and writes their hits to one contiguous
-            //     stretch (order inside the list is irrelevant: all sums below are trees), so
-            //     the divergent bit loop runs max-over-lanes(total hits), not sum-of-maxima.
-            unsigned wd[TL_WORDS / 32];
+            //     stretch (order inside the list is irrelevant: all sums below are trees).  The
+            //     bits are visited by a uniform, fully unrolled loop with predicated stores --
+            //     no divergence and no per-hit popc/ffs on the XU pipe.  (A loop over the SET
+            //     bits of each lane's words spent 17 % of the kernel's instructions here at 6.8
+            //     active lanes; ranking lane = bit with two popc per word was no faster.)
+            constexpr int NW = TL_WORDS / 32;
+            unsigned wd[NW];
             int c = 0;
 #pragma unroll
-            for (int j = 0; j < TL_WORDS / 32; j++) {
+            for (int j = 0; j < NW; j++) {
                 const int q = j * 32 + lane;
                 wd[j] = q < ng ? s_mask[q * TL_MSTRIDE + tsel] : 0u;
                 c += __popc(wd[j]);
@@ -349,33 +356,23 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
             }
             const int nU = __shfl_sync(FULL_MASK, incl, 31);
             if (nU <= TL_UCAP) {
-                // one loop body for all of a lane's words (a shift register of words), so
-                // lanes working on different words still issue together
-                constexpr int NW = TL_WORDS / 32;
-                int off = incl - c, qbase = lane * 32, left = NW;
-                unsigned word = wd[0];
-                for (;;) {
-                    if (word == 0) {
-                        if (--left == 0) break;
+                unsigned short *out = ul + (incl - c);
 #pragma unroll
-                        for (int j = 0; j + 1 < NW; j++) wd[j] = wd[j + 1];   // registers: shift down
-                        wd[NW - 1] = 0;
-                        word = wd[0];
-                        qbase += 32 * 32;
-                        continue;
-                    }
-                    const unsigned low = word & (0u - word);
-                    word ^= low;
-                    ul[off++] = (unsigned short)(qbase + s_bit[(low * 0x077CB531u) >> 27]);
+                for (int j = 0; j < NW; j++) {
+                    if (j * 32 >= ng) break;               // warp-uniform
+                    const unsigned word = wd[j];
+                    const int sbase = (j * 32 + lane) * 32;
+#pragma unroll
+                    for (int b = 0; b < 32; b++)
+                        if (word & (1u << b)) *out++ = (unsigned short)(sbase + b);
                 }
             }
-            if (nU > TL_UCAP) { hand_back(i); continue; }
+            if (nU > TL_UCAP) { hand_back(i, 1); continue; }
             __syncwarp();
 
             // (2) classify every hit, build the separation list, sum the displacement
             int cntA = 0, cntB = 0, cntW = 0;      // cntA, cntW: per-lane until reduced below
             bool ranges_ok = true;                 // every separation fit for the hoisted divide
-            bool displaced = false;                // a hit underneath a displaced reference node
             float sx = 0, sy = 0, sz = 0;
             const float Af = (float)A;
             for (int base = 0; base < nU; base += 32) {
@@ -394,8 +391,15 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                     if (dz > boxhalf) dz = __fsub_rn(dz, box);
                 }
                 const float r2 = sq3_nofma(dx, dy, dz);                          // tree.c:88
-                const bool inA = live && r2 < hA2, inB = live && r2 < hB2, inW = live && r2 < hsw2;
-                displaced |= (inB | inW) & df_flagged(pj.w);
+                bool inA = live && r2 < hA2, inB = live && r2 < hB2, inW = live && r2 < hsw2;
+                if ((inB | inW) && df_flagged(pj.w)) {
+                    // underneath a displaced reference node (defect.cuh): Find_ngb_tree finds it
+                    // only if every node of its path opens at the radius of that search
+                    const float4 *path = a.dnodes + a.dmap[gidx];
+                    if (inA) inA = defect_open(path, pi.x, pi.y, pi.z, hA, box, boxhalf);
+                    if (inB) inB = inA || defect_open(path, pi.x, pi.y, pi.z, hB, box, boxhalf);
+                    if (inW) inW = defect_open(path, pi.x, pi.y, pi.z, hsw, box, boxhalf);
+                }
                 const unsigned mB = __ballot_sync(FULL_MASK, inB);
                 if (MODE & MODE_DENSITY) {
                     if (inB) {
@@ -429,8 +433,6 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
             }
             ranges_ok = __all_sync(FULL_MASK, ranges_ok);
             __syncwarp();
-            // the open tests of defect.cuh depend on the search radius: generic path
-            if (__any_sync(FULL_MASK, displaced)) { hand_back(i); continue; }
 
             float h = hA, rho = 0, drho = 0;
             bool ok = true;
@@ -457,11 +459,13 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 } else if (cntB >= TG_DESNNGB && cntB <= TL_LCAP) {   // second search, 1.23*Hsml
                     cnt = cntB; h = hB; c_search += 2;
                 } else ok = false;                           // a third search: generic path
+                int why = 3;                                 // a third search / list overflow
                 if (ok) {
                     __syncwarp();
                     ok = find_hsml(a, L, cnt, h, rho, drho, c_evals, c_iters, ranges_ok);
+                    why = 4;                                 // no convergence on the frozen list
                 }
-                if (!ok) { hand_back(i); continue; }
+                if (!ok) { hand_back(i, why); continue; }
             }
             c_search += (MODE & MODE_WVT) ? 1 : 0;
             c_gath += max(cnt, cntW);

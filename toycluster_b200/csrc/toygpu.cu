@@ -290,9 +290,9 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     CUC(dmalloc(&c->partial, (size_t)2 * c->npartial));
     CUC(dmalloc(&c->scal, 4));
     CUC(dmalloc(&c->flags, 8));
-    CUC(dmalloc(&c->counters, 4));
+    CUC(dmalloc(&c->counters, 12));
     CUC(cudaMemsetAsync(c->flags, 0, 8 * sizeof(int), c->stream));
-    CUC(cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    CUC(cudaMemsetAsync(c->counters, 0, 12 * sizeof(unsigned long long), c->stream));
 
     // sweep grid: every SM full of resident blocks (persistent, work-stealing)
     cudaDeviceProp prop;
@@ -485,7 +485,7 @@ extern "C" int tg_set_apot(tg_ctx *c, const float *apot)
 
 static int reset_counters(tg_ctx *c)
 {
-    CU(cudaMemsetAsync(c->counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    CU(cudaMemsetAsync(c->counters, 0, 12 * sizeof(unsigned long long), c->stream));
     CU(cudaMemsetAsync(c->flags + 1, 0, sizeof(int), c->stream));   // sweep status
     CU(cudaMemsetAsync(c->flags + 5, 0, sizeof(int), c->stream));   // handed-back count
     c->launches = 0;
@@ -730,7 +730,7 @@ static int move_pass(tg_ctx *c, double scale)
 
 static int finish_stats(tg_ctx *c, bool have_sweep_events)
 {
-    unsigned long long h[4];
+    unsigned long long h[9];
     int nwork = 0;
     CU(cudaMemcpyAsync(h, c->counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(&nwork, c->flags + 5, sizeof nwork, cudaMemcpyDeviceToHost, c->stream));
@@ -741,6 +741,7 @@ static int finish_stats(tg_ctx *c, bool have_sweep_events)
     c->stats.gathered = h[1];
     c->stats.searches = h[2];
     c->stats.hsml_iters = h[3];
+    for (int k = 0; k < 5; k++) c->stats.handback_why[k] = h[4 + k];
     c->stats.kernels = c->launches;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
