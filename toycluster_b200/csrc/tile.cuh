@@ -63,7 +63,8 @@
 #define TL_OFF_RUN (TL_OFF_MASK + TL_WORDS * TL_MSTRIDE * 4)
 #define TL_OFF_RL (TL_OFF_RUN + TL_RUNS * 4)
 #define TL_OFF_MISC (TL_OFF_RL + TL_WARPS * TL_CAP * 8)
-#define TL_SMEM (TL_OFF_MISC + 64)             // misc: 2 ints, 32-byte bit-index table at +16
+#define TL_OFF_WQ (TL_OFF_MISC + 64)           // misc: 2 ints
+#define TL_SMEM (TL_OFF_WQ + TL_WARPS * 128)   // per warp: queue of 64 displacement partners
 
 // Periodic gap^2 between two boxes (centre/half-width form).
 static __device__ __forceinline__ float box_box_dist2(float ax, float ay, float az, float ahx,
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
     double *rl = (double *)(smem + TL_OFF_RL) + w * TL_CAP;
     unsigned short *ul = (unsigned short *)(rl + (TL_CAP / 4) * 3);   // last quarter of the region
     TileList L{rl};
+    unsigned short *wq = (unsigned short *)(smem + TL_OFF_WQ) + w * 64;
 
     const float norm = (float)pow(TG_DESNNGB / *a.vsum / K_FOURPITHIRD, 1.0 / 3.0);   // wvt_relax.c:120
     const float box = a.bx.box_f, boxhalf = a.bx.boxhalf_f;
@@ -375,6 +377,18 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
             bool ranges_ok = true;                 // every separation fit for the hoisted divide
             float sx = 0, sy = 0, sz = 0;
             const float Af = (float)A;
+            int qn = 0;                            // queued displacement partners (candidate slots)
+            auto wvt_batch = [&](int cntq) {       // wvt_relax.c:137-170 for wq[0 .. cntq)
+                if (lane < cntq) {
+                    const int sl = wq[lane];
+                    const float4 pj = a.pw[s_run[sl >> 3] + (sl & 7)];
+                    float tx, ty, tz;
+                    if (wvt_pair_fast(pi, pj, hi_w, norm, Af, binv_hi, binv_lo, tx, ty, tz)) {
+                        sx += tx; sy += ty; sz += tz;
+                        c_pairs++;
+                    }
+                }
+            };
             for (int base = 0; base < nU; base += 32) {
                 const int k = base + lane;
                 const bool live = k < nU;
@@ -416,16 +430,26 @@ __global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs
                 cntB += __popc(mB);
                 cntW += inW;
                 if (MODE & MODE_WVT) {
-                    // nU <= TL_CAP < NGBMAX: the list cut of tree.c:91 cannot bite here
-                    if (inW && gidx != i) {                                      // wvt_relax.c:141
-                        float tx, ty, tz;
-                        if (wvt_pair_fast(pi, pj, hi_w, norm, Af, binv_hi, binv_lo, tx, ty, tz)) {
-                            sx += tx; sy += ty; sz += tz;
-                            c_pairs++;
-                        }
+                    // nU <= TL_CAP < NGBMAX: the list cut of tree.c:91 cannot bite here.
+                    // Only about half of the hits are displacement partners, so they are queued
+                    // and evaluated 32 at a time with full lanes.
+                    const bool useW = inW && gidx != i;                          // wvt_relax.c:141
+                    const unsigned mW = __ballot_sync(FULL_MASK, useW);
+                    if (useW) wq[qn + __popc(mW & lt)] = (unsigned short)slot;
+                    qn += __popc(mW);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        wvt_batch(32);
+                        qn -= 32;
+                        __syncwarp();
+                        const unsigned short rest = wq[32 + lane];
+                        __syncwarp();
+                        wq[lane] = rest;
+                        __syncwarp();
                     }
                 }
             }
+            if ((MODE & MODE_WVT) && qn > 0) wvt_batch(qn);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 cntA += __shfl_xor_sync(FULL_MASK, cntA, o);
