@@ -1,0 +1,21 @@
+"""Time A/B builds (scripts/variants.sh) on the 10 M merger: one process per variant."""
+import os, subprocess, sys, glob
+here = os.path.dirname(os.path.abspath(__file__))
+root = os.path.dirname(here)
+code = '''
+import sys; sys.path.insert(0, %r)
+import toycluster_b200 as tc
+from toycluster_b200 import workloads
+import numpy as np
+w = workloads.make("merger_1e7")
+g = tc.HotPath.from_workload(w); g.upload(w.pos)
+ms = []
+for it in range(7):
+    g.wvt_iteration(0.0085); s = g.stats(); ms.append((s["step_ms"], s["sweep_ms"]))
+o = g.download()
+print("step %%.2f sweep %%.2f  checksum %%.6f" %% (np.mean([m[0] for m in ms[3:]]), np.mean([m[1] for m in ms[3:]]), float(o["pos"].astype(np.float64).sum() + o["hsml"].astype(np.float64).sum())))
+''' % root
+libs = sorted(glob.glob(os.path.join(root, "toycluster_b200", "variants", "*.so")))
+for lib in [os.path.join(root, "toycluster_b200", "libtoygpu.so")] + libs:
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, TOYGPU_LIB=lib), capture_output=True, text=True)
+    print(os.path.basename(lib), r.stdout.strip(), r.stderr.strip()[-300:])

@@ -95,10 +95,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ToyGpuError(f"{LIB_PATH} missing: run toycluster_b200.build() "
+    path = os.environ.get("TOYGPU_LIB", LIB_PATH)      # developer knob: A/B builds of the kernels
+    if not os.path.exists(path):
+        raise ToyGpuError(f"{path} missing: run toycluster_b200.build() "
                           "(make -C toycluster_b200/csrc)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.tg_last_error.restype = C.c_char_p
     lib.tg_last_error.argtypes = [C.c_void_p]
     lib.tg_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Config)]

@@ -34,6 +34,13 @@
 //   larger caps 640 runs / 768 hits (13.3: fewer hand-backs but a smaller L1 carve-out),
 //   smaller caps (13.2-15.3: hand-backs), software-pipelined candidate fetch (13.1),
 //   per-sub-run candidate lists (only 23 % fewer candidates for a second bit matrix).
+// 10 M-particle merger, whole step ms: 129.6 | packed FP32 (FADD2/FMUL2/FFMA2) in Find_hsml
+//   and phase 1 121.0 | hit-list expansion as a uniform unrolled bit loop (was a loop over set
+//   bits: 17 % of all instructions at 6.8 active lanes) 112.2 | displacement partners queued
+//   for full-lane evaluation 110.8.  Tried and dropped: lane = bit expansion with two popc per
+//   word (120.7: the XU pipe), Hsml entries first + separations of the "1.23*Hsml only" hits
+//   deferred to the second search + skipping them in Find_hsml iterations below Hsml (121.6:
+//   13 % fewer kernel evaluations, but the second gather of those hits is exposed L2 latency).
 #pragma once
 #include "common.cuh"
 #include "bvh.cuh"
