@@ -102,15 +102,25 @@ static __device__ __forceinline__ float tile_radius(float hA, float hw_raw, floa
 // take the generic path.  An entry is (level-0 box << 4) | mask of its four 8-particle runs
 // that lie within reach of the tile.  "Reach" is tested run against run: the tile's own four
 // sub-boxes, each with the largest radius of its 8 targets, against the candidate's four.
-// One warp per tile.
-__global__ void k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw,
-                            const float *__restrict__ hsml_in, const double *__restrict__ vsum,
-                            int tile_lo, int tile_hi, int *__restrict__ tile_ng,
-                            int *__restrict__ tile_groups)
+// One warp per tile.  The hierarchy is descended BREADTH first, level by level, through a
+// per-warp queue in shared memory: the accepted nodes of a level stay in ascending order
+// (ballot compaction), so the result equals the ordered depth-first walk, but a level's box
+// tests are independent loads instead of one dependent chain per visited node -- the
+// depth-first version spent ~300 serialised L2 round trips per tile (5.2 ms per step at 10 M).
+#define TW_WARPS 8
+#define TW_QCAP 320                      // accepted nodes per level a tile may have (TL_ENT + slack)
+
+__global__ void __launch_bounds__(TW_WARPS * 32)
+k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw, const float *__restrict__ hsml_in,
+            const double *__restrict__ vsum, int tile_lo, int tile_hi, int *__restrict__ tile_ng,
+            int *__restrict__ tile_groups)
 {
-    const int tile = tile_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    __shared__ int s_queue[TW_WARPS][2][TW_QCAP];
+    const int wib = threadIdx.x >> 5;
+    const int tile = tile_lo + blockIdx.x * TW_WARPS + wib;
     if (tile >= tile_hi) return;
     const int lane = lane_id();
+    const unsigned lt = (1u << lane) - 1;
     const int i = tile * 32 + lane;
     const float norm = (float)pow(TG_DESNNGB / *vsum / K_FOURPITHIRD, 1.0 / 3.0);
 
@@ -134,33 +144,81 @@ __global__ void k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw,
     const float ax = t.cx[tile], ay = t.cy[tile], az = t.cz[tile];
     const float ahx = t.hx[tile], ahy = t.hy[tile], ahz = t.hz[tile];
     const float R2 = R * R * 1.00001f;
-    // lane = (tile run a, candidate run b): a = lane >> 2 (lanes 0..15 used), b = lane & 3
-    const int ra = (lane >> 2) & 3, rb = lane & 3;
+    auto test = [&](int o) -> bool {
+        return box_box_dist2(ax, ay, az, ahx, ahy, ahz, t.cx[o], t.cy[o], t.cz[o], t.hx[o], t.hy[o],
+                             t.hz[o], bx.box_f, bx.boxhalf_f) <= R2;
+    };
+
+    // ---- descend: queue of accepted nodes per level, ascending -------------------------
+    int *cur = s_queue[wib][0], *nxt = s_queue[wib][1];
+    int ncur;
+    {
+        const int level = t.top;
+        const bool hit = lane < t.lvl_n[level] && test(t.lvl_off[level] + lane);
+        const unsigned m = __ballot_sync(FULL_MASK, hit);
+        if (hit) cur[__popc(m & lt)] = lane;
+        ncur = __popc(m);
+    }
+    bool overflow = false;
+    for (int level = t.top - 1; level >= 0 && !overflow; level--) {
+        __syncwarp();
+        const int off = t.lvl_off[level], nl = t.lvl_n[level];
+        int nnext = 0;
+        for (int p = 0; p < ncur; p += 2) {              // two parents in flight
+            const int k0 = cur[p] * 32 + lane;
+            const int k1 = p + 1 < ncur ? cur[p + 1] * 32 + lane : nl;
+            const bool h0 = k0 < nl && test(off + k0);
+            const bool h1 = k1 < nl && test(off + k1);
+            const unsigned m0 = __ballot_sync(FULL_MASK, h0), m1 = __ballot_sync(FULL_MASK, h1);
+            const int c0 = __popc(m0), c1 = __popc(m1);
+            if (nnext + c0 + c1 > TW_QCAP) { overflow = true; break; }
+            if (h0) nxt[nnext + __popc(m0 & lt)] = k0;
+            if (h1) nxt[nnext + c0 + __popc(m1 & lt)] = k1;
+            nnext += c0 + c1;
+        }
+        int *sw = cur; cur = nxt; nxt = sw;
+        ncur = nnext;
+    }
+    __syncwarp();
+    if (overflow) {
+        if (lane == 0) tile_ng[tile] = -2;
+        return;
+    }
+
+    // ---- level-0 boxes: run against run, two boxes per pass (one per half warp) ---------
+    // lane & 15 = (tile run a, candidate run b): a = bits 2-3, b = bits 0-1
+    const int ra = (lane >> 2) & 3, rb = lane & 3, half = lane >> 4;
     const int sa = 4 * tile + ra;
     const float tx = t.scx[sa], ty = t.scy[sa], tz = t.scz[sa];
     const float thx = t.shx[sa], thy = t.shy[sa], thz = t.shz[sa];
     const float Ra = __shfl_sync(FULL_MASK, Rsub, ra * 8);
     const float Ra2 = Ra * Ra * 1.00001f;
-
     int ng = 0, nruns = 0;
     int *out = tile_groups + (size_t)tile * TL_ENT;
-    bvh_walk_pred(t, [&](int o) -> bool {
-        return box_box_dist2(ax, ay, az, ahx, ahy, ahz, t.cx[o], t.cy[o], t.cz[o], t.hx[o], t.hy[o],
-                             t.hz[o], bx.box_f, bx.boxhalf_f) <= R2;
-    }, [&](int g) -> bool {
+#pragma unroll 4
+    for (int j = 0; j < ncur; j += 2) {
+        const bool have = j + half < ncur;
+        const int g = have ? cur[j + half] : 0;
         const int sb = 4 * g + rb;
-        const bool near = lane < 16 &&
+        const bool near = have &&
             box_box_dist2(tx, ty, tz, thx, thy, thz, t.scx[sb], t.scy[sb], t.scz[sb], t.shx[sb],
                           t.shy[sb], t.shz[sb], bx.box_f, bx.boxhalf_f) <= Ra2;
-        unsigned m = __ballot_sync(FULL_MASK, near);
-        m = (m | (m >> 4) | (m >> 8) | (m >> 12)) & 0xfu;
-        if (m) {
-            if (ng < TL_ENT && lane == 0) out[ng] = (g << 4) | (int)m;
+        const unsigned m = __ballot_sync(FULL_MASK, near);
+        const unsigned lo16 = m & 0xffffu, hi16 = m >> 16;
+        const unsigned m0 = (lo16 | (lo16 >> 4) | (lo16 >> 8) | (lo16 >> 12)) & 0xfu;
+        const unsigned m1 = (hi16 | (hi16 >> 4) | (hi16 >> 8) | (hi16 >> 12)) & 0xfu;
+        const int g0 = __shfl_sync(FULL_MASK, g, 0), g1 = __shfl_sync(FULL_MASK, g, 16);
+        if (m0) {
+            if (ng < TL_ENT && lane == 0) out[ng] = (g0 << 4) | (int)m0;
             ng++;
-            nruns += __popc(m);
+            nruns += __popc(m0);
         }
-        return ng < 8192;        // keep counting past the cap: the count feeds diagnostics
-    });
+        if (m1) {
+            if (ng < TL_ENT && lane == 0) out[ng] = (g1 << 4) | (int)m1;
+            ng++;
+            nruns += __popc(m1);
+        }
+    }
     if (lane == 0) {
         if (ng > TL_ENT || nruns > TL_RUNS) tile_ng[tile] = -max(nruns, 2);
         else {

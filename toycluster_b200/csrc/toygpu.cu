@@ -642,7 +642,7 @@ template <int MODE> static int launch_tiled(tg_ctx *c, SweepArgs a)
     if (tile_hi <= tile_lo) return TG_OK;
     CU(cudaMemsetAsync(c->flags, 0, sizeof(int), c->stream));
     CU(cudaMemsetAsync(c->flags + 5, 0, 2 * sizeof(int), c->stream));
-    k_tile_walk<<<cdiv((long long)(tile_hi - tile_lo) * 32, 256), 256, 0, c->stream>>>(
+    k_tile_walk<<<cdiv(tile_hi - tile_lo, TW_WARPS), TW_WARPS * 32, 0, c->stream>>>(
         c->bvh, c->box, c->pw, c->hsml_in, c->scal, tile_lo, tile_hi, c->tile_ng, c->tile_groups);
     LAUNCH_CHECK();
     a.next = c->flags;
