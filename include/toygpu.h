@@ -156,6 +156,24 @@ int tg_wvt_scratch(tg_ctx *ctx, float *hsml_wvt, float *delta /* [n][3] */);
 
 int tg_get_stats(tg_ctx *ctx, tg_stats *out);
 
+/* Make_magnetic_field() == magnetic_field.c:12-131 in one call: vector potential
+ * A = max_halos (rho_gas / Rho0)^eta per particle (:33-69), B = rot A (the sweep of
+ * tg_bfld_from_rotA), normalisation to bfld_norm / sqrt(3) at the field maximum and the cap at
+ * bmax_main (bmax_sub for particles Halo_containing() puts into a halo with index > 1)
+ * (:71-131).  Needs the index of the last tg_find_sph_quantities.  The arrays have one entry per
+ * row of tg_set_halos: Halo[j].R_Sample[0], Halo[j].R_Sample[1], Halo[j].Is_Stripped. */
+typedef struct {
+    double bfld_norm, bfld_eta;          /* Param.Bfld_Norm, Param.Bfld_Eta */
+    double bmax_main, bmax_sub;          /* BMAX = 18e-6 and 2e-6 (magnetic_field.c:4,113) */
+    int sub_first;                       /* Sub.First */
+    const double *r_sample_gas;
+    const double *r_sample_dm;
+    const int *is_stripped;
+} tg_bfield;
+int tg_make_magnetic_field(tg_ctx *ctx, const tg_bfield *par, double *norm_out, int *n_limited_out);
+/* Apot of the current order, apot[n][3] (what tg_make_magnetic_field or tg_set_apot left). */
+int tg_get_apot(tg_ctx *ctx, float *apot);
+
 /* ---- test hooks (parity with peano.c / sort.c / tree.c) ----------------------------- */
 /* Peano_Key of every uploaded particle, upload order (peano.c:63-71). */
 int tg_peano_keys(tg_ctx *ctx, uint64_t *hi, uint64_t *lo);

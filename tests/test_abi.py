@@ -33,12 +33,20 @@ def test_library_exports_every_declared_symbol():
     assert set(tc.EXPORTS) <= set(_declared())
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors have the sizes gcc gives the structs of include/toygpu.h."""
+    import subprocess
     from toycluster_b200 import api
-    # tg_config: int,int,double*3,unsigned,int,int,void* ; tg_stats: 5 u64, 2 double, 1 u64
-    assert ctypes.sizeof(api._Config) == 56
-    assert ctypes.sizeof(api.Stats) == 64
-    assert ctypes.sizeof(api._Halo) == 72
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "toygpu.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n",'
+                   'sizeof(tg_config), sizeof(tg_stats), sizeof(tg_halo), sizeof(tg_bfield),'
+                   'sizeof(tg_exchange));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    want = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    got = [ctypes.sizeof(c) for c in (api._Config, api.Stats, api._Halo, api._BField, api._Exchange)]
+    assert got == want, (got, want)
+    assert want[0] == 56 and want[2] == 72
 
 
 def test_no_cpu_fallback():

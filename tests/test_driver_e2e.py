@@ -14,6 +14,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFDIR = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
 CPU, GPU = os.path.join(REFDIR, "Toycluster_cpu"), os.path.join(REFDIR, "Toycluster_gpu")
+GPU_B = os.path.join(REFDIR, "Toycluster_gpu_b")      # ... with Make_magnetic_field on the device too
 
 PAR = """Output_file ./{out}
 Ntotal      {ntotal}
@@ -23,7 +24,7 @@ ImpactParam 50
 ZeroEOrbitFrac 0.8
 Cuspy       0
 Redshift	0.87
-Bfld_Norm   20e-6
+Bfld_Norm   {bnorm}
 Bfld_Eta    0.5
 Bfld_Scale  100
 bf          0.17
@@ -64,7 +65,7 @@ needs_drivers = pytest.mark.skipif(not (os.path.exists(CPU) and os.path.exists(G
 
 @needs_drivers
 def test_cpu_driver_runs_and_writes_all_blocks(tmp_path):
-    (tmp_path / "a.par").write_text(PAR.format(out="IC_a", ntotal=6000, mass_ratio=0))
+    (tmp_path / "a.par").write_text(PAR.format(out="IC_a", ntotal=6000, mass_ratio=0, bnorm="20e-6"))
     out = run(CPU, "a.par", tmp_path, {})
     assert "Starting iterative SPH regularisation" in out and "#00: Err max=" in out
     b = read_gadget2(tmp_path / "IC_a")
@@ -74,16 +75,32 @@ def test_cpu_driver_runs_and_writes_all_blocks(tmp_path):
 
 @pytest.mark.gpu
 @needs_drivers
-@pytest.mark.parametrize("mass_ratio,ntotal", [(0, 20000), (0.3125, 24000)])
-def test_gpu_driver_writes_the_same_gadget_file(tmp_path, mass_ratio, ntotal):
-    (tmp_path / "c.par").write_text(PAR.format(out="IC_c", ntotal=ntotal, mass_ratio=mass_ratio))
-    (tmp_path / "g.par").write_text(PAR.format(out="IC_g", ntotal=ntotal, mass_ratio=mass_ratio))
+@pytest.mark.parametrize("mass_ratio,ntotal,exe,bnorm", [
+    (0, 20000, GPU, "20e-6"), (0.3125, 24000, GPU, "20e-6"),
+    (0.3125, 24000, GPU_B, "20e-6"),
+    (0, 20000, GPU_B, "60e-6")])        # strong field: the cap of magnetic_field.c:115-125 bites
+def test_gpu_driver_writes_the_same_gadget_file(tmp_path, mass_ratio, ntotal, exe, bnorm):
+    (tmp_path / "c.par").write_text(PAR.format(out="IC_c", ntotal=ntotal, mass_ratio=mass_ratio, bnorm=bnorm))
+    (tmp_path / "g.par").write_text(PAR.format(out="IC_g", ntotal=ntotal, mass_ratio=mass_ratio, bnorm=bnorm))
     out_c = run(CPU, "c.par", tmp_path, {})
-    out_g = run(GPU, "g.par", tmp_path, {"TOYGPU_FLAGS": "1"})      # TG_WVT_SEQUENTIAL
+    out_g = run(exe, "g.par", tmp_path, {"TOYGPU_FLAGS": "1"})      # TG_WVT_SEQUENTIAL
     # the per-iteration log lines of wvt_relax.c:91-92, as printed
     it_c = [l for l in out_c.splitlines() if l.lstrip().startswith("#")]
     it_g = [l for l in out_g.splitlines() if l.lstrip().startswith("#")]
     assert len(it_c) >= 3 and it_c == it_g
+    # magnetic_field.c:90,129 print the normalisation and the number of capped particles
+    for key in ("Bfld Norm =", "Bfld of "):
+        lc = [l for l in out_c.splitlines() if l.startswith(key)]
+        lg = [l for l in out_g.splitlines() if l.startswith(key)]
+        assert len(lc) == 1 and len(lg) == 1
+        if key == "Bfld of ":
+            nc, ng_ = int(lc[0].split()[2]), int(lg[0].split()[2])
+            assert abs(nc - ng_) <= max(2, nc // 200)       # B within 1e-5: a few sit on the cap
+            if bnorm != "20e-6":
+                assert nc > 10
+        else:
+            vc, vg = float(lc[0].split("=")[1]), float(lg[0].split("=")[1])
+            assert abs(vc - vg) <= 2e-5 * abs(vc)
     c, g = read_gadget2(tmp_path / "IC_c"), read_gadget2(tmp_path / "IC_g")
     assert list(c) == list(g)
     for label in c:

@@ -47,6 +47,13 @@ class _Config(C.Structure):
                 ("rank", C.c_int), ("nranks", C.c_int), ("stream", C.c_void_p)]
 
 
+class _BField(C.Structure):
+    _fields_ = [("bfld_norm", C.c_double), ("bfld_eta", C.c_double), ("bmax_main", C.c_double),
+                ("bmax_sub", C.c_double), ("sub_first", C.c_int),
+                ("r_sample_gas", C.POINTER(C.c_double)), ("r_sample_dm", C.POINTER(C.c_double)),
+                ("is_stripped", C.POINTER(C.c_int))]
+
+
 class Stats(C.Structure):
     _fields_ = [("pair_evals", C.c_ulonglong), ("gathered", C.c_ulonglong),
                 ("searches", C.c_ulonglong), ("hsml_iters", C.c_ulonglong),
@@ -74,6 +81,7 @@ EXPORTS = [
     "tg_upload_soa_slice", "tg_set_cold", "tg_download_soa_slice", "tg_set_apot", "tg_download", "tg_download_soa", "tg_find_sph_quantities", "tg_regularise",
     "tg_bfld_from_rotA", "tg_wvt_iteration", "tg_wvt_begin", "tg_wvt_finish", "tg_wvt_scratch", "tg_get_stats", "tg_peano_keys",
     "tg_sort", "tg_find_ngb", "tg_guess_hsml", "tg_get_exchange",
+    "tg_make_magnetic_field", "tg_get_apot",
 ]
 
 _lib = None
@@ -129,6 +137,9 @@ def load():
     lib.tg_find_ngb.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
     lib.tg_guess_hsml.argtypes = [C.c_void_p, C.c_void_p]
     lib.tg_get_exchange.argtypes = [C.c_void_p, C.POINTER(_Exchange)]
+    lib.tg_make_magnetic_field.argtypes = [C.c_void_p, C.POINTER(_BField), C.POINTER(C.c_double),
+                                           C.POINTER(C.c_int)]
+    lib.tg_get_apot.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -159,6 +170,7 @@ class HotPath:
             h.rho0, h.beta, h.rcore, h.rcut = r[3], r[4], r[5], r[6]
             h.cuspy, h.mass_gas = int(r[7]), r[8]
         self._check(self.lib.tg_set_halos(self._ctx, len(rows), halos))
+        self.nhalos = len(rows)
 
     @classmethod
     def from_workload(cls, w, **kw):
@@ -255,6 +267,27 @@ class HotPath:
 
     def bfld_from_rotA_sph(self):
         self._check(self.lib.tg_bfld_from_rotA(self._ctx))
+
+    def make_magnetic_field(self, bfld_norm, bfld_eta, r_sample_gas=None, r_sample_dm=None,
+                            is_stripped=None, sub_first=None, bmax_main=18e-6, bmax_sub=2e-6):
+        """Make_magnetic_field() (magnetic_field.c:12-131) -> (norm, particles capped); B and A
+        stay on the device (download(bfld=True), get_apot())."""
+        nh = self.nhalos
+        gas = np.ascontiguousarray(np.zeros(nh) if r_sample_gas is None else r_sample_gas, np.float64)
+        dm = np.ascontiguousarray(np.zeros(nh) if r_sample_dm is None else r_sample_dm, np.float64)
+        st = np.ascontiguousarray(np.zeros(nh) if is_stripped is None else is_stripped, np.int32)
+        par = _BField(bfld_norm, bfld_eta, bmax_main, bmax_sub,
+                      nh if sub_first is None else int(sub_first),
+                      gas.ctypes.data_as(C.POINTER(C.c_double)), dm.ctypes.data_as(C.POINTER(C.c_double)),
+                      st.ctypes.data_as(C.POINTER(C.c_int)))
+        norm, cnt = C.c_double(), C.c_int()
+        self._check(self.lib.tg_make_magnetic_field(self._ctx, C.byref(par), C.byref(norm), C.byref(cnt)))
+        return norm.value, cnt.value
+
+    def get_apot(self):
+        out = np.empty((self.n, 3), np.float32)
+        self._check(self.lib.tg_get_apot(self._ctx, _ptr(out)))
+        return out
 
     def wvt_iteration(self, step):
         emax, emean = C.c_double(), C.c_double()

@@ -28,6 +28,7 @@
 #include "guess.cuh"
 #include "sph.cuh"
 #include "tile.cuh"
+#include "bfield.cuh"
 
 static thread_local std::string g_create_error;
 
@@ -893,6 +894,76 @@ extern "C" int tg_bfld_from_rotA(tg_ctx *c)
     CU(cudaEventRecord(c->ev[3], c->stream));
     CU(cudaEventRecord(c->ev[1], c->stream));
     return finish_stats(c, true);
+}
+
+extern "C" int tg_make_magnetic_field(tg_ctx *c, const tg_bfield *par, double *norm_out, int *n_limited_out)
+{
+    if (!c || !par) return TG_EINVAL;
+    if (!c->index_valid) return fail(c, TG_EINVAL, "tg_make_magnetic_field: no index (call tg_find_sph_quantities first)");
+    if (c->nhalos == 0) return fail(c, TG_EINVAL, "tg_set_halos has not been called");
+    CU(cudaSetDevice(c->cfg.device));
+    const int n = c->n, T = 256;
+    if (!c->apot) {
+        CU(dmalloc(&c->apot, (size_t)3 * n));
+        CU(dmalloc(&c->apot_s, (size_t)3 * n));
+    }
+    std::vector<HaloExtra> ex(c->nhalos);
+    for (int j = 0; j < c->nhalos; j++) {
+        ex[j].r_sample_gas = par->r_sample_gas ? par->r_sample_gas[j] : 0;
+        ex[j].r_sample_dm = par->r_sample_dm ? par->r_sample_dm[j] : 0;
+        ex[j].is_stripped = par->is_stripped ? par->is_stripped[j] : 0;
+    }
+    HaloExtra *dex = nullptr;
+    int *dcnt = nullptr;
+    CU(dmalloc(&dex, c->nhalos));
+    CU(dmalloc(&dcnt, 1));
+    CU(cudaMemcpyAsync(dex, ex.data(), sizeof(HaloExtra) * c->nhalos, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(dcnt, 0, sizeof(int), c->stream));
+    int rc = reset_counters(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    k_vector_potential<<<cdiv(n, T), T, 0, c->stream>>>(n, c->pw, c->halos, c->nhalos, c->box.boxhalf_f,
+                                                       par->bfld_eta, c->apot);
+    LAUNCH_CHECK();
+    c->have_apot = true;
+    SweepArgs a = sweep_args(c, 0);
+    a.hsml_in = c->hsml_out;    // SphP.Hsml as left by the density call
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    if ((rc = launch_sweep<MODE_ROTA>(c, a))) return rc;
+    CU(cudaEventRecord(c->ev[3], c->stream));
+    const int nb = cdiv(n, RED_THREADS);
+    k_bfld_max<<<nb, RED_THREADS, 0, c->stream>>>(n, c->bfld, c->partial);
+    LAUNCH_CHECK();
+    k_bfld_max_final<<<1, RED_THREADS, 0, c->stream>>>(nb, c->partial, c->scal + 3);
+    LAUNCH_CHECK();
+    double max_b2 = 0;
+    CU(cudaMemcpyAsync(&max_b2, c->scal + 3, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const double norm = par->bfld_norm / sqrt(max_b2) / sqrt(3.0);     // magnetic_field.c:88-90
+    k_bfld_normalise<<<cdiv(n, T), T, 0, c->stream>>>(n, c->pw, c->bfld, norm, c->box.boxhalf_f, c->halos, dex,
+                                                     c->nhalos, par->sub_first, c->box.box_d,
+                                                     par->bmax_main, par->bmax_sub, dcnt);
+    LAUNCH_CHECK();
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    int cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, dcnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    rc = finish_stats(c, true);
+    cudaFree(dex);
+    cudaFree(dcnt);
+    if (rc) return rc;
+    if (norm_out) *norm_out = norm;
+    if (n_limited_out) *n_limited_out = cnt;
+    return TG_OK;
+}
+
+extern "C" int tg_get_apot(tg_ctx *c, float *apot)
+{
+    if (!c || !apot) return TG_EINVAL;
+    if (!c->have_apot) return fail(c, TG_EINVAL, "tg_get_apot: Apot not set");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaMemcpyAsync(apot, c->apot, sizeof(float) * 3 * c->n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return TG_OK;
 }
 
 extern "C" int tg_get_stats(tg_ctx *c, tg_stats *out)

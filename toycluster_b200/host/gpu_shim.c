@@ -131,6 +131,59 @@ void Bfld_from_rotA_SPH()
     fflush(stdout);
 }
 
+#ifdef TOYGPU_SHIM_MAGNETIC_FIELD
+/* magnetic_field.c:12-31: with this defined the shim also replaces
+ * magnetic_field.o -- vector potential, rot(A), normalisation and cap run on the device in one
+ * call, and Apot / Bfld cross the bus once. */
+void Make_magnetic_field()
+{
+    printf("Magnetic field: \n"
+           "   B0              = %g G\n"
+           "   eta             = %g \n\n", Param.Bfld_Norm, Param.Bfld_Eta);
+    printf("Constructing B from rot(A)");
+    fflush(stdout);
+
+    ensure_context();
+    const int n = Param.Npart[0], nh = Param.Nhalos;
+    double *rs_gas = Malloc(nh * sizeof *rs_gas), *rs_dm = Malloc(nh * sizeof *rs_dm);
+    int *stripped = Malloc(nh * sizeof *stripped);
+    for (int j = 0; j < nh; j++) {
+        rs_gas[j] = Halo[j].R_Sample[0];
+        rs_dm[j] = Halo[j].R_Sample[1];
+        stripped[j] = Halo[j].Is_Stripped;
+    }
+    tg_bfield par;
+    memset(&par, 0, sizeof par);
+    par.bfld_norm = Param.Bfld_Norm;
+    par.bfld_eta = Param.Bfld_Eta;
+    par.bmax_main = 18e-6;                   /* BMAX, magnetic_field.c:4 */
+    par.bmax_sub = 2e-6;                     /* magnetic_field.c:113 */
+    par.sub_first = Sub.First;
+    par.r_sample_gas = rs_gas;
+    par.r_sample_dm = rs_dm;
+    par.is_stripped = stripped;
+    double norm = 0;
+    int limited = 0;
+    check(tg_make_magnetic_field(Ctx, &par, &norm, &limited), "tg_make_magnetic_field");
+
+    float *buf = Malloc((size_t)3 * n * sizeof *buf);
+    check(tg_get_apot(Ctx, buf), "tg_get_apot");
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++)
+            SphP[i].Apot[k] = buf[3 * (size_t)i + k];
+    check(tg_download_soa(Ctx, NULL, NULL, NULL, NULL, NULL, NULL, buf), "tg_download_soa");
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++)
+            SphP[i].Bfld[k] = buf[3 * (size_t)i + k];
+    Free(buf); Free(rs_gas); Free(rs_dm); Free(stripped);
+
+    printf(" done \n\n");
+    printf("Bfld Norm = %g \n", norm);
+    printf("Bfld of %d particles limited to %g G\n", limited, 18e-6);
+    fflush(stdout);
+}
+#endif
+
 /* wvt_relax.c:227-256; host-side, for callers outside the path (proto.h:46). */
 float Global_density_model(const int ipart)
 {
