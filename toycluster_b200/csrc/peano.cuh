@@ -13,6 +13,10 @@
 
 struct Transposed { uint64_t a, b, c; };   // X[0], X[1], X[2] after the transform
 
+// LOW = lowest bit plane the caller reads.  Plane q of the transform only rewrites bits below q
+// and the Gray code only propagates from high to low bits, so planes below LOW can be left
+// undone: the bits >= LOW of the result are those of the full loop (peano.c:140-162 runs to 1).
+template <int LOW = 1>
 static __device__ __forceinline__ Transposed hilbert_transpose(double x, double y, double z)
 {
     const double scale = 9223372036854775808.0;   // 2^63
@@ -21,7 +25,7 @@ static __device__ __forceinline__ Transposed hilbert_transpose(double x, double 
     uint64_t c = __double2ull_rz(x * scale);
 
     // planes 63 .. 1: conditional invert of the low bits of `a`, or exchange with b / c
-    for (int plane = 63; plane >= 1; plane--) {
+    for (int plane = 63; plane >= (LOW > 1 ? LOW : 1); plane--) {
         const uint64_t q = 1ull << plane;
         const uint64_t low = q - 1;
 
@@ -50,7 +54,7 @@ static __device__ __forceinline__ Transposed hilbert_transpose(double x, double 
 static __device__ __forceinline__ void peano_key(double x, double y, double z,
                                                  uint64_t &hi, uint64_t &lo)
 {
-    const Transposed T = hilbert_transpose(x, y, z);
+    const Transposed T = hilbert_transpose<21>(x, y, z);
     uint64_t h = 0, l = 0;
     // planes 62..21 -> 126 bits; the first 21 triplets + 1 bit land in hi.
 #pragma unroll 1
@@ -69,7 +73,7 @@ static __device__ __forceinline__ void peano_key(double x, double y, double z,
 static __device__ __forceinline__ void reversed_peano_key(double x, double y, double z,
                                                           uint64_t &hi, uint64_t &lo)
 {
-    const Transposed T = hilbert_transpose(x, y, z);
+    const Transposed T = hilbert_transpose<20>(x, y, z);
     uint64_t h = 0, l = 0;
 #pragma unroll 1
     for (int plane = 20; plane <= 62; plane++) {

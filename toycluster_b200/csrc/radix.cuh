@@ -168,30 +168,34 @@ k_radix_scatter(int n, const uint64_t *__restrict__ keys_in, const int *__restri
     }
 }
 
-// After the 64-bit sort: order runs of equal key_hi by (key_lo, index). One thread per run
-// start; runs are a handful of particles at most, so a serial insertion sort is fine.
-__global__ void k_fix_ties(int n, const uint64_t *__restrict__ hi_sorted, int *__restrict__ idx,
-                           const uint64_t *__restrict__ key_lo, int *__restrict__ n_tied)
+// After the radix passes over the top `64 - low_bits` bits of key_hi: order every run of keys
+// that agree in those bits by (key_hi, key_lo, index).  One thread per run start; runs are a
+// handful of particles at most (the sorted bits resolve cells of 2^-16 Boxsize or finer), so a
+// serial insertion sort is fine.  hi_sorted is permuted along with idx.
+__global__ void k_fix_ties(int n, uint64_t *__restrict__ hi_sorted, int *__restrict__ idx,
+                           const uint64_t *__restrict__ key_lo, int low_bits, int *__restrict__ n_tied)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const uint64_t h = hi_sorted[k];
-    if (k > 0 && hi_sorted[k - 1] == h) return;      // not a run start
-    if (k + 1 >= n || hi_sorted[k + 1] != h) return;  // run of one
+    const uint64_t h = hi_sorted[k] >> low_bits;
+    if (k > 0 && (hi_sorted[k - 1] >> low_bits) == h) return;      // not a run start
+    if (k + 1 >= n || (hi_sorted[k + 1] >> low_bits) != h) return;  // run of one
     int end = k + 1;
-    while (end < n && hi_sorted[end] == h) end++;
+    while (end < n && (hi_sorted[end] >> low_bits) == h) end++;
     atomicAdd(n_tied, end - k);
     for (int a = k + 1; a < end; a++) {
         const int ia = idx[a];
-        const uint64_t la = key_lo[ia];
+        const uint64_t ha = hi_sorted[a], la = key_lo[ia];
         int b = a - 1;
         while (b >= k) {
             const int ib = idx[b];
-            const uint64_t lb = key_lo[ib];
-            if (lb < la || (lb == la && ib < ia)) break;
+            const uint64_t hb = hi_sorted[b], lb = key_lo[ib];
+            if (hb < ha || (hb == ha && (lb < la || (lb == la && ib < ia)))) break;
             idx[b + 1] = ib;
+            hi_sorted[b + 1] = hb;
             b--;
         }
         idx[b + 1] = ia;
+        hi_sorted[b + 1] = ha;
     }
 }

@@ -503,7 +503,13 @@ static int sort_keys(tg_ctx *c)
     LAUNCH_CHECK();
     uint64_t *kin = c->key_hi, *kout = c->key_tmp;
     int *iin = c->idx, *iout = c->idx_tmp;
-    for (int shift = 0; shift < 64; shift += RS_BITS) {
+    // Only the top bits need radix passes: 8 tree levels beyond log8(n) leave runs of a few
+    // keys at most, and k_fix_ties orders every run by the full 128-bit key anyway.
+    int levels = 8;
+    for (long long m = 1; m < n; m *= 8) levels++;
+    int low_bits = 64 - std::min(64, (3 * levels + RS_BITS - 1) / RS_BITS * RS_BITS);
+    if (getenv("TOYGPU_FULL_SORT")) low_bits = 0;
+    for (int shift = low_bits; shift < 64; shift += RS_BITS) {
         k_radix_hist<<<c->ntiles, RS_THREADS, 0, c->stream>>>(n, kin, shift, c->ntiles, c->hist);
         LAUNCH_CHECK();
         unsigned *bin_total = c->hist + (size_t)RS_BINS * c->ntiles;
@@ -517,7 +523,7 @@ static int sort_keys(tg_ctx *c)
     }
     c->key_hi_s = kin;
     c->idx_s = iin;
-    k_fix_ties<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->idx_s, c->key_lo, c->flags + 3);
+    k_fix_ties<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->idx_s, c->key_lo, low_bits, c->flags + 3);
     LAUNCH_CHECK();
     return TG_OK;
 }
