@@ -6,8 +6,8 @@ cd "$(dirname "$0")/../toycluster_b200/csrc"
 mkdir -p ../variants
 while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
-  nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC $flags \
-       -shared -Xlinker -soname=libtoygpu.so -o ../variants/libtoygpu_$name.so toygpu.cu &
+  nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fopenmp $flags \
+       -shared -Xlinker -soname=libtoygpu.so -o ../variants/libtoygpu_$name.so toygpu.cu -lgomp &
 done
 wait
 ls -la ../variants

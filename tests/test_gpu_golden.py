@@ -184,3 +184,46 @@ def test_error_paths_and_edges():
     assert np.array_equal(got["id"], want["id"])
     for k in ("hsml", "rho", "varhsml"):
         assert np.array_equal(got[k], want[k]), k
+
+
+def test_make_magnetic_field_equals_its_three_stages():
+    """tg_make_magnetic_field (magnetic_field.c:12-131 on the device) against the same three
+    stages done separately: the vector potential restated in numpy, the rot(A) operator that
+    test_golden_final_density_and_rotA pins against the reference, and the normalisation /
+    cap in numpy.  (The whole-program check is tests/test_driver_e2e.py.)"""
+    from toycluster_b200 import workloads
+    w = workloads.make("merger_1e6", n_gas=12288)
+    g = tc.HotPath.from_workload(w)
+    g.upload(w.pos)
+    g.find_sph_quantities()
+    o = g.download()
+    pos = o["pos"]
+    boxhalf = np.float32(0.5 * w.boxsize)
+    # magnetic_field.c:33-69
+    amax = np.zeros(len(pos))
+    for h in w.halos:
+        if h.mass_gas == 0:
+            continue
+        d = (pos.astype(np.float64) - np.asarray(h.dcom) - np.float64(boxhalf)).astype(np.float32)
+        r2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]          # float expression
+        rho = workloads.gas_density_profile(np.sqrt(r2.astype(np.float64)), h.rho0, h.beta, h.rcore, h.rcut)
+        amax = np.maximum(amax, np.power(rho / h.rho0, 0.5))
+    apot = np.repeat(amax.astype(np.float32)[:, None], 3, 1)
+    g.set_apot(apot)
+    g.bfld_from_rotA_sph()
+    b = g.download(bfld=True)["bfld"]
+    for bnorm in (20e-6, 80e-6):
+        norm, capped = g.make_magnetic_field(bnorm, 0.5)
+        got_a, got_b = g.get_apot(), g.download(bfld=True)["bfld"]
+        assert (got_a == apot).mean() > 0.999 and np.abs(got_a - apot).max() <= 1e-6 * apot.max()
+        b2 = ((b[:, 0] * b[:, 0] + b[:, 1] * b[:, 1]) + b[:, 2] * b[:, 2]).astype(np.float64)
+        want_norm = bnorm / np.sqrt(b2.max()) / np.sqrt(3.0)
+        assert abs(norm - want_norm) <= 1e-6 * want_norm
+        wb = (b.astype(np.float64) * want_norm).astype(np.float32)
+        B2 = ((wb[:, 0] * wb[:, 0] + wb[:, 1] * wb[:, 1]) + wb[:, 2] * wb[:, 2]).astype(np.float64)
+        over = B2 > 18e-6 ** 2
+        wb[over] = (wb[over].astype(np.float64) * (18e-6 / np.sqrt(B2[over]))[:, None]).astype(np.float32)
+        assert abs(capped - int(over.sum())) <= 2
+        assert (capped > 0) == (bnorm > 40e-6)
+        scale = np.abs(wb).max()
+        assert np.abs(got_b - wb).max() <= 2e-6 * scale
