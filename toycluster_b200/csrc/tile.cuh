@@ -40,14 +40,22 @@
 //   for full-lane evaluation 110.8.  Tried and dropped: lane = bit expansion with two popc per
 //   word (120.7: the XU pipe), Hsml entries first + separations of the "1.23*Hsml only" hits
 //   deferred to the second search + skipping them in Find_hsml iterations below Hsml (121.6:
-//   13 % fewer kernel evaluations, but the second gather of those hits is exposed L2 latency).
+//   13 % fewer kernel evaluations, but the second gather of those hits is exposed L2 latency),
+//   6 / 5 / 4 / 12 warps per block at 4 / 4 / 5 / 2 blocks per SM (112.6 / 114.1 / 113.5 / 114.6
+//   against 108.9 for 8 x 3), four list entries per lane and iteration in Find_hsml (111.4),
+//   caps 640 and 768 hits (108.6, 110.4).
 #pragma once
 #include "common.cuh"
 #include "bvh.cuh"
 #include "sph.cuh"
 #include "f32x2.cuh"
 
+#ifndef TL_WARPS
 #define TL_WARPS 8
+#endif
+#ifndef TL_BLOCKS
+#define TL_BLOCKS 3                      // resident blocks per SM the kernel is compiled for
+#endif
 #ifndef TL_ENT
 #define TL_ENT 256                       // candidate level-0 boxes per tile (global list entries)
 #endif
@@ -290,7 +298,7 @@ struct TileList {     // density list: r as double; the sign bit marks "outside 
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TL_WARPS * 32, 3) k_sweep_tile(const SweepArgs a, int tile_lo,
+__global__ void __launch_bounds__(TL_WARPS * 32, TL_BLOCKS) k_sweep_tile(const SweepArgs a, int tile_lo,
                                                                    int tile_hi)
 {
     extern __shared__ __align__(16) unsigned char smem[];
