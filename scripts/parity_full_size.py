@@ -10,7 +10,7 @@ from oracle import ref
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 niter = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-w = workloads.make("merger_1e6", n_gas=n)
+w = workloads.make("merger_1e7" if n > 2_000_000 else "merger_1e6", n_gas=n)
 r = ref.Ref(w.n_gas, w.boxsize, w.mpart_gas, w.mtotal, w.halo_table(), 0)
 r.load(w.pos)
 snaps, stamps = [], []
