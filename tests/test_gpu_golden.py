@@ -227,3 +227,27 @@ def test_make_magnetic_field_equals_its_three_stages():
         assert (capped > 0) == (bnorm > 40e-6)
         scale = np.abs(wb).max()
         assert np.abs(got_b - wb).max() <= 2e-6 * scale
+
+
+def test_sort_with_long_runs_of_nearly_equal_keys():
+    """The radix passes only cover the top key bits; runs that agree in them are ordered by the
+    full 128-bit key (and equal keys by upload index) in k_fix_ties.  Clumps of particles a
+    few parsec apart make such runs long and frequent."""
+    from oracle import port
+    w = workloads.make("merger_1e6", n_gas=2000)
+    rng = np.random.default_rng(11)
+    base = w.pos[:2000]
+    clumps = [base]
+    for _ in range(5):
+        clumps.append((base + rng.uniform(-3e-3, 3e-3, base.shape)).astype(np.float32))
+    pos = np.clip(np.concatenate(clumps), 0, np.float32(w.boxsize)).astype(np.float32)
+    pos[7000] = pos[123]                      # bit-identical positions: tie broken by index
+    pos[9000] = pos[123]
+    n = len(pos)
+    g = tc.HotPath(n, w.boxsize, w.mpart_gas, w.mtotal, w.halo_table())
+    g.upload(pos)
+    perm = g.sort()
+    want, hi, lo, dup = port.sort(pos, w.boxsize)
+    assert dup >= 2
+    assert np.array_equal(perm, want)
+    assert np.array_equal(g.download()["pos"], pos[want])
