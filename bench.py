@@ -194,6 +194,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()            # the library launches on this stream, so the
     torch.cuda.set_stream(stream)           # events below see exactly its kernels
