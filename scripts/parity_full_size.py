@@ -23,9 +23,23 @@ def cb(it):
     return 0
 t0 = time.perf_counter(); r.regularise(niter, cb); t_ref = time.perf_counter() - t0
 log = ref.parse_log(r.log())
+niter = min(niter, len(snaps) - 1)          # the reference may terminate by itself (wvt_relax.c:95-98)
+import math
+def exact_step(printed, base=0.0085):
+    """The log prints step with %g (6 digits); the value itself is base * 0.8 * 0.8 * ... in
+    double (wvt_relax.c:100)."""
+    m = round(math.log(printed / base) / math.log(0.8))
+    v = base
+    for _ in range(m):
+        v *= 0.8
+    assert abs(v - printed) <= 1e-5 * printed
+    return v
+for row in log:
+    row["step"] = exact_step(row["step"])
 out = {"n_gas": n, "iterations": niter, "reference_threads": r.nthreads,
        "reference_s_per_iteration": list(np.diff(stamps))}
-for mode, flags in (("sequential", tc.WVT_SEQUENTIAL), ("default", 0)):
+modes = (("sequential", tc.WVT_SEQUENTIAL), ("default", 0)) if len(sys.argv) < 4 else ((sys.argv[3], tc.WVT_SEQUENTIAL if sys.argv[3] == "sequential" else 0),)
+for mode, flags in modes:
     g = tc.HotPath.from_workload(w, flags=flags)
     g.upload(w.pos)
     rows = []
