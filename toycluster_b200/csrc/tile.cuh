@@ -8,7 +8,7 @@
 //
 //   k_tile_walk   one warp per tile: R = max over the tile of the largest radius any of its
 //                 targets can need without a third search (1.23*Hsml, sph.c:51, and the WVT
-//                 radius, wvt_relax.c:135); ordered walk with a box-to-box distance test, at
+//                 radius, wvt_relax.c:135); breadth-first descent (order kept) with a box-to-box distance test, at
 //                 the leaves run-against-run on 8-particle sub-boxes -> ascending list of
 //                 (box, run mask) entries in global memory (~370 runs = 2900 candidates).
 //   k_sweep_tile  one 8-warp block per tile, 3 blocks per SM:
@@ -18,9 +18,10 @@
 //              a shared-memory bit matrix.  No divergence, no ballots, no per-target walk.
 //     phase 2  one WARP per target: expand the target's bit row into a compact hit list,
 //              re-evaluate every hit with the exact FMA-free predicate against Hsml,
-//              1.23*Hsml and the WVT radius, build the FP64 separation list with full lanes,
-//              run Find_hsml (sph.c:80-214) and the displacement sum (wvt_relax.c:137-170)
-//              -- the same device functions as the generic sweep.
+//              1.23*Hsml and the WVT radius (and, for a hit underneath a displaced reference
+//              node, the open tests of defect.cuh), build the FP64 separation list with full
+//              lanes, queue the displacement partners and evaluate them 32 at a time, run
+//              Find_hsml (sph.c:80-214) -- the same device functions as the generic sweep.
 //   Anything outside the fast path's envelope (cold start, list overflow, a third search,
 //   Find_hsml not converging on the frozen list) is pushed to a work list and redone from
 //   scratch by the generic kernel, so results do not depend on which path ran

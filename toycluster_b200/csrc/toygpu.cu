@@ -4,11 +4,14 @@
 //   state   posh  float4[n]  (x, y, z, Hsml) of the current order       16 B
 //           id    int[n]     upload index of the particle               4 B
 //   sort    key_hi/key_lo u64[n], idx int[n] (+ ping-pong copies)
-//   sorted  pw    float4[n]  (x, y, z, raw WVT hsml) -- the one array the sweep gathers
+//   sorted  pw    float4[n]  (x, y, z, raw WVT hsml; sign bit of w = displaced-node flag) --
+//                            the one array the sweep gathers
+//           soa   float[3][n8] x, y, z again, for the packed phase 1 of the tile sweep
 //           hsml_in, rho_model float[n], key_hi_s/key_lo_s u64[n]
 //   result  hsml_out, rho, varhsml float[n], delta float[3][n], bfld float[n][3]
-//   index   6 float arrays of ~n/31 boxes
-// About 150 B per particle: 1.5 GB at 10 M, far inside 180 GB.
+//   index   6 float arrays of ~n/31 boxes (+ 4 sub-boxes per level-0 box), tile candidate lists
+//   defect  dmap int[n], path nodes float4[max(2^20, n/2)] (defect.cuh)
+// About 200 B per particle: 2 GB at 10 M, far inside 180 GB.
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
