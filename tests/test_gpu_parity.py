@@ -269,3 +269,34 @@ def test_substructure_halo_table():
         for k in ("rho_model", "hsml", "rho", "varhsml", "pos"):
             assert np.array_equal(o[k], s[k]), (it, k, (o[k] != s[k]).mean())
         assert np.array_equal(hw, s["hw"]) and np.array_equal(dl, s["delta"])
+
+
+@pytest.mark.parametrize("name,n,seed", [("merger_1e6", 30011, 11), ("single_1e5", 70000, 12),
+                                         ("merger_1e6", 150003, 7)])
+def test_sequential_mode_other_seeds_and_ragged_sizes(name, n, seed):
+    """More of test_wvt_iterations_sequential_bit_exact (scripts/fuzz_parity.py runs hundreds of
+    these).  The last case is the one that exposed `step*hsml*wk*dx/r` being formed as
+    `(step*hsml*wk/r)*dx`: one displacement component of one particle in its last bit."""
+    w = workloads.make(name, n_gas=n, seed=seed)
+    r = ref.Ref(w.n_gas, w.boxsize, w.mpart_gas, w.mtotal, w.halo_table(), REF_THREADS)
+    r.load(w.pos)
+    after = []
+
+    def cb(it):
+        s = r.read()
+        if it > 0:
+            s["hw"], s["delta"] = r.wvt_scratch()
+            after.append(s)
+        return 0
+
+    niter = 3
+    r.regularise(niter + 1, cb)
+    g = tc.HotPath.from_workload(w, flags=tc.WVT_SEQUENTIAL)
+    g.upload(w.pos)
+    for it in range(niter):
+        g.wvt_iteration(0.0085)                      # wvt_relax.c:51; unchanged before iteration 3
+        s, o = after[it], g.download()
+        hw, dl = g.wvt_scratch()
+        for k in ("id", "rho_model", "hsml", "rho", "varhsml", "pos"):
+            assert np.array_equal(o[k], s[k]), (it, k)
+        assert np.array_equal(hw, s["hw"]) and np.array_equal(dl, s["delta"]), it

@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(TL_WARPS * 32, TL_BLOCKS) k_sweep_tile(const S
                 int why = 3;                                 // a third search / list overflow
                 if (ok) {
                     __syncwarp();
-                    ok = find_hsml(a, L, cnt, h, rho, drho, c_evals, c_iters, ranges_ok);
+                    ok = find_hsml<(MODE & MODE_EXACT) != 0>(a, L, cnt, h, rho, drho, c_evals, c_iters, ranges_ok);
                     why = 4;                                 // no convergence on the frozen list
                 }
                 if (!ok) { hand_back(i, why); continue; }

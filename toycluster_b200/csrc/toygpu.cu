@@ -308,6 +308,8 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
             return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         };
         CUC(set((const void *)k_sweep<MODE_DENSITY, false>));
+        CUC(set((const void *)k_sweep<MODE_DENSITY | MODE_EXACT, false>));
+        CUC(set((const void *)k_sweep<MODE_DENSITY | MODE_EXACT, true>));
         CUC(set((const void *)k_sweep<MODE_WVT, false>));
         CUC(set((const void *)k_sweep<MODE_WVT_SEQ, false>));
         CUC(set((const void *)k_sweep<MODE_DENSITY | MODE_WVT, false>));
@@ -325,6 +327,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
             return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM);
         };
         CUC(set((const void *)k_sweep_tile<MODE_DENSITY>));
+        CUC(set((const void *)k_sweep_tile<MODE_DENSITY | MODE_EXACT>));
         CUC(set((const void *)k_sweep_tile<MODE_WVT>));
         CUC(set((const void *)k_sweep_tile<MODE_DENSITY | MODE_WVT>));
         int tile_per_sm = 1;
@@ -667,7 +670,8 @@ template <int MODE> static int launch_tiled(tg_ctx *c, SweepArgs a)
 
 template <int MODE> static int launch_sweep(tg_ctx *c, const SweepArgs &a)
 {
-    constexpr bool tileable = MODE == MODE_DENSITY || MODE == MODE_WVT || MODE == (MODE_DENSITY | MODE_WVT);
+    constexpr bool tileable = MODE == MODE_DENSITY || MODE == (MODE_DENSITY | MODE_EXACT) || MODE == MODE_WVT ||
+                              MODE == (MODE_DENSITY | MODE_WVT);
     if constexpr (tileable) {
         if (c->use_tiles && !c->any_cold) return launch_tiled<MODE>(c, a);
     }
@@ -691,7 +695,9 @@ static int check_flags(tg_ctx *c)
 static int density_pass(tg_ctx *c)
 {
     SweepArgs a = sweep_args(c, 0);
-    int rc = launch_sweep<MODE_DENSITY>(c, a);
+    // the sequential parity mode also forms Find_hsml's kernels operation for operation
+    int rc = (c->cfg.flags & TG_WVT_SEQUENTIAL) ? launch_sweep<MODE_DENSITY | MODE_EXACT>(c, a)
+                                                : launch_sweep<MODE_DENSITY>(c, a);
     if (rc) return rc;
     c->any_cold = false;
     return TG_OK;
