@@ -10,10 +10,14 @@ from oracle import ref
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 240.0
 t0 = time.time(); bad = 0; ncase = 0
-cases = itertools.product(range(1, 100), ("merger_1e6", "single_1e5", "merger_1e7"), (30011, 70000, 150003), (0, 300))
-for seed, name, n, snap in cases:
+cases = itertools.product(range(1, 100), ("merger_1e6", "single_1e5"), (30011, 70000, 150003), (0, 300), (0, 1))
+for seed, name, n, snap, shift in cases:
     if time.time() - t0 > budget: break
     w = workloads.make(name, n_gas=n, seed=seed)
+    if shift:      # periodic shift: the cluster straddles the box faces, every wrap path is taken
+        off = np.random.default_rng(seed).uniform(0, w.boxsize, 3)
+        w.pos = np.mod(w.pos.astype(np.float64) + off, w.boxsize).astype(np.float32)
+        w.pos[w.pos >= np.float32(w.boxsize)] = 0
     if snap: w.pos = workloads.snap_to_cell_planes(w.pos, w.boxsize, snap, seed=seed)
     r = ref.Ref(w.n_gas, w.boxsize, w.mpart_gas, w.mtotal, w.halo_table(), 16)
     r.load(w.pos); after = []
@@ -36,6 +40,6 @@ for seed, name, n, snap in cases:
         if not np.array_equal(hw, s["hw"]) or not np.array_equal(dl, s["delta"]):
             ok = False; print("   MISMATCH", it, "hw/delta", int((dl != s["delta"]).any(1).sum()))
     ncase += 1; bad += not ok
-    print("%-11s n=%6d seed=%2d snap=%3d displaced=%4d handed_back=%s %s" % (name, n, seed, snap, g.stats()["displaced_particles"], hb, "ok" if ok else "FAIL"), flush=True)
+    print("%-11s n=%6d seed=%2d snap=%3d shift=%d displaced=%4d handed_back=%s %s" % (name, n, seed, snap, shift, g.stats()["displaced_particles"], hb, "ok" if ok else "FAIL"), flush=True)
 print("cases", ncase, "failed", bad)
 sys.exit(1 if bad else 0)

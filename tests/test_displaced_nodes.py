@@ -168,3 +168,45 @@ def test_gpu_default_mode_and_rotA_with_displaced_nodes(wl):
     got = g.download(bfld=True)["bfld"]
     scale = np.abs(want).max(axis=1, keepdims=True) + 1e-30
     assert (np.abs(got - want) / scale).max() < 1e-5
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_gpu_particle_on_the_box_face_is_filed_elsewhere():
+    """Pos == Boxsize is legal (the wrap of wvt_relax.c:200 is inclusive) but scales to 2^63,
+    whose Peano key is not the key of the cell the particle sits in: the reference files it in
+    a leaf somewhere else and its neighbours do not find it.  Found by scripts/fuzz_parity.py
+    with periodically shifted inputs."""
+    w = workloads.make("merger_1e6", n_gas=20011, seed=5)
+    off = np.array([0.31, 0.57, 0.83]) * w.boxsize
+    pos = np.mod(w.pos.astype(np.float64) + off, w.boxsize).astype(np.float32)
+    pos[pos >= np.float32(w.boxsize)] = 0
+    # the densest region now straddles the faces: put a few of its particles exactly ON a face
+    d = np.abs(pos - np.float32(w.boxsize)).min(axis=1)
+    pick = np.argsort(d)[:6]
+    for j, i in enumerate(pick):
+        pos[i, j % 3] = np.float32(w.boxsize)
+    w.pos = pos
+    r = _ref(w, 8)
+    r.load(w.pos)
+    after = []
+
+    def cb(it):
+        s = r.read()
+        if it > 0:
+            s["hw"], s["delta"] = r.wvt_scratch()
+            after.append(s)
+        return 0
+
+    r.regularise(3, cb)
+    g = tc.HotPath.from_workload(w, flags=tc.WVT_SEQUENTIAL)
+    g.upload(w.pos)
+    for it in range(2):
+        g.wvt_iteration(0.0085)
+        if it == 0:
+            assert g.stats()["displaced_particles"] >= 6
+        s, o = after[it], g.download()
+        hw, dl = g.wvt_scratch()
+        for k in ("id", "rho_model", "hsml", "rho", "varhsml", "pos"):
+            assert np.array_equal(o[k], s[k]), (it, k, int((o[k] != s[k]).sum()))
+        assert np.array_equal(dl, s["delta"]), it

@@ -16,6 +16,10 @@
 // and for a path whose centres are where the keys say, the open test cannot fail for a
 // particle within reach.  So only particles underneath a displaced node need their path:
 //
+// A second way into the same situation: a coordinate equal to Boxsize scales to 2^63, whose key
+// is not the key of the cell the particle sits in (peano.cuh), so the reference files the
+// particle in a leaf somewhere else in the box.  It gets its own path (event level DF_SELF).
+//
 //   k_defect_detect  one thread per particle i: i creates the nodes of levels
 //                    cpl[i]+1 .. max(cpl[i], cpl[i+1])+1 (cpl = common key triplets with the
 //                    predecessor, guess.cuh).  Follow i's own coordinate bits down the float
@@ -37,6 +41,7 @@
 #include "guess.cuh"
 
 #define DF_MAX_LEVEL 30
+#define DF_SELF 99                  // event level: only the particle itself needs a path
 
 struct DefectTab {
     int2 *events;        // (first particle, level)
@@ -66,12 +71,22 @@ __global__ void k_defect_detect(int n, const float4 *__restrict__ pw, double box
     const int c0 = cpl[i], c1 = i + 1 < n ? (int)cpl[i + 1] : -1;
     const int lo = max(c0 + 1, 1);
     const int hi = min(max(c0, c1) + 1, DF_MAX_LEVEL);
-    if (hi < lo) return;
     const float4 p = pw[i];
     const double scale = 9223372036854775808.0;   // 2^63, peano.c:134-136
     const uint64_t X = __double2ull_rz((double)p.x / box * scale);
     const uint64_t Y = __double2ull_rz((double)p.y / box * scale);
     const uint64_t Z = __double2ull_rz((double)p.z / box * scale);
+    if ((X | Y | Z) >> 63) {
+        // A coordinate equal to Boxsize (legal: the wrap of wvt_relax.c:200 is inclusive) scales
+        // to 2^63, whose key is NOT that of the cell the particle sits in (peano.cuh): the
+        // reference files the particle in a leaf somewhere else in the box, and finds it only
+        // from there.  Its own literal path reproduces that; level DF_SELF = just this particle.
+        const int e = atomicAdd(&d.counts[0], 1);
+        if (e < d.cap_events) d.events[e] = make_int2(i, DF_SELF);
+        // ... and the nodes it creates are placed by its position, far from their other members:
+        // the sign test below disagrees with its (all-zero) low bits and flags them
+    }
+    if (hi < lo) return;
     float cx = (float)(box / 2), cy = cx, cz = cx;     // tree.c:133
     for (int q = 1; q <= hi; q++) {
         const bool bx = (X >> (63 - q)) & 1, by = (Y >> (63 - q)) & 1, bz = (Z >> (63 - q)) & 1;
@@ -162,7 +177,8 @@ __global__ void k_defect_paths(int n, float4 *__restrict__ pw, double box,
             const int2 ev = d.events[e];
             const int i = ev.x, m = ev.y;
             int end = i;
-            if (df_leaf_level(i, n, cpl) >= m) {       // else the node was collapsed away
+            if (m == DF_SELF) end = i + 1;
+            else if (df_leaf_level(i, n, cpl) >= m) {  // else the node was collapsed away
                 // one past the last particle of i's level-m cell
                 uint64_t mh, ml;
                 df_mask(m, mh, ml);
