@@ -210,3 +210,37 @@ def test_gpu_particle_on_the_box_face_is_filed_elsewhere():
         for k in ("id", "rho_model", "hsml", "rho", "varhsml", "pos"):
             assert np.array_equal(o[k], s[k]), (it, k, int((o[k] != s[k]).sum()))
         assert np.array_equal(dl, s["delta"]), it
+
+
+@needs_ref
+def test_port_files_a_particle_on_the_box_face_like_the_reference():
+    """CPU: a coordinate equal to Boxsize has the key of 2^63, not of its cell; the restated
+    tree (like the reference's) then misses the particle from where it really is."""
+    w = workloads.make("merger_1e6", n_gas=6000, seed=5)
+    pos = np.mod(w.pos.astype(np.float64) + np.array([0.31, 0.57, 0.83]) * w.boxsize, w.boxsize).astype(np.float32)
+    pos[pos >= np.float32(w.boxsize)] = 0
+    pick = np.argsort(np.abs(pos - np.float32(w.boxsize)).min(axis=1))[:4]
+    for j, i in enumerate(pick):
+        pos[i, j % 3] = np.float32(w.boxsize)
+    w.pos = pos
+    r = _ref(w)
+    r.load(w.pos)
+    r.find_sph_quantities()
+    d = r.read()
+    o = port.find_sph_quantities(w, w.pos)
+    for k in ("id", "pos", "hsml", "rho", "varhsml"):
+        assert np.array_equal(o[k], d[k]), k
+    on_face = np.flatnonzero((d["pos"] == np.float32(w.boxsize)).any(axis=1))
+    assert len(on_face) >= 4
+    missed = 0
+    for i in on_face:
+        # its nearest neighbours look for it with a generous radius
+        dist = np.abs(d["pos"] - d["pos"][i])
+        dist = np.minimum(dist, np.float32(w.boxsize) - dist)
+        near = np.argsort((dist ** 2).sum(1))[1:6]
+        for t in near:
+            h = float(2 * d["hsml"][t])
+            a, s = r.find_ngb_tree(int(t), h), r.find_ngb_simple(int(t), h)
+            assert np.array_equal(port.find_ngb(d["pos"], w.boxsize, int(t), h), a)
+            missed += (i in s) and (i not in a)
+    assert missed > 0
