@@ -9,8 +9,10 @@ from toycluster_b200 import workloads
 from oracle import ref
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 240.0
+sizes = tuple(int(v) for v in sys.argv[2].split(",")) if len(sys.argv) > 2 else (30011, 70000, 150003)
+seed0 = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 t0 = time.time(); bad = 0; ncase = 0
-cases = itertools.product(range(1, 100), ("merger_1e6", "single_1e5"), (30011, 70000, 150003), (0, 300), (0, 1))
+cases = itertools.product(range(seed0, 100), ("merger_1e6", "single_1e5"), sizes, (0, 300), (0, 1))
 for seed, name, n, snap, shift in cases:
     if time.time() - t0 > budget: break
     w = workloads.make(name, n_gas=n, seed=seed)
