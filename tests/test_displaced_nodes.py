@@ -244,3 +244,32 @@ def test_port_files_a_particle_on_the_box_face_like_the_reference():
             assert np.array_equal(port.find_ngb(d["pos"], w.boxsize, int(t), h), a)
             missed += (i in s) and (i not in a)
     assert missed > 0
+
+
+@pytest.mark.gpu
+def test_gpu_lattice_input_overflows_the_event_table_gracefully():
+    """A lattice whose planes are cell-centre planes displaces nodes everywhere: far more events
+    than the table holds.  The run must complete, say so in tg_stats, and stay finite; with
+    TG_EXACT_NEIGHBOURS nothing is flagged at all."""
+    w = workloads.make("single_1e5", n_gas=32768)
+    k = np.arange(32, dtype=np.float64)
+    gx, gy, gz = np.meshgrid(k, k, k, indexing="ij")
+    lattice = np.stack([gx, gy, gz], -1).reshape(-1, 3) / 32 * w.boxsize     # j/32: every point on a centre plane
+    rng = np.random.default_rng(3)
+    pos = lattice.astype(np.float32)
+    jitter = rng.uniform(-0.2, 0.2, pos.shape) * w.boxsize / 32
+    move = rng.random(len(pos)) < 0.5                     # half the particles leave the planes
+    pos[move] = np.mod(pos[move].astype(np.float64) + jitter[move], w.boxsize).astype(np.float32)
+    pos = np.clip(pos, 0, np.float32(w.boxsize))
+    g = tc.HotPath.from_workload(w)
+    g.upload(pos)
+    g.find_sph_quantities()
+    st = g.stats()
+    assert st["displaced_nodes"] > 4096 and st["displaced_overflow"] == 1, st
+    o = g.download()
+    assert np.isfinite(o["hsml"]).all() and np.isfinite(o["rho"]).all() and (o["hsml"] > 0).all()
+    e = tc.HotPath.from_workload(w, flags=tc.EXACT_NEIGHBOURS)
+    e.upload(pos)
+    e.find_sph_quantities()
+    assert e.stats()["displaced_nodes"] == 0 and e.stats()["displaced_overflow"] == 0
+    assert np.isfinite(e.download()["rho"]).all()
