@@ -9,8 +9,9 @@
 // Each pass is three kernels over tiles of RS_TILE keys:
 //   k_radix_hist    per-tile digit histogram -> hist[digit][tile]
 //   k_radix_scan    exclusive scan of each digit's row (one block per digit) + digit totals
-//   k_radix_scatter stable rank of every key inside its tile (warp match + per-warp counters)
-//                   and scatter to hist[digit][tile] + rank
+//   k_radix_scatter stable rank of every key inside its tile (warp match + per-warp counters),
+//                   the tile staged in digit order in shared memory, then written out so that
+//                   each digit's run lands at hist[digit][tile] as one segment
 #pragma once
 #include "common.cuh"
 
@@ -98,6 +99,11 @@ k_radix_scatter(int n, const uint64_t *__restrict__ keys_in, const int *__restri
 {
     __shared__ unsigned cnt[RS_WARPS][RS_BINS];   // per-warp digit counters -> warp offsets
     __shared__ unsigned bin_base[RS_BINS];        // exclusive scan of the digit totals
+    __shared__ unsigned local_excl[RS_BINS];      // start of each digit's run inside the tile
+    __shared__ unsigned gbase[RS_BINS];           // ... and in the output
+    __shared__ unsigned warp_tot[RS_WARPS];
+    __shared__ uint64_t s_key[RS_TILE];
+    __shared__ int s_val[RS_TILE];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int b = threadIdx.x; b < RS_WARPS * RS_BINS; b += RS_THREADS) (&cnt[0][0])[b] = 0;
     {   // RS_THREADS == RS_BINS: thread d scans bin_total[0..d)
@@ -144,26 +150,56 @@ k_radix_scatter(int n, const uint64_t *__restrict__ keys_in, const int *__restri
     }
     __syncthreads();
 
-    // exclusive prefix over warps for every digit, plus the tile's global offset
-    for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) {
-        unsigned run = bin_base[d] + hist[(size_t)d * ntiles + blockIdx.x];
+    // Per digit: offsets of the warps inside the digit's run, the run's start inside the tile
+    // (exclusive scan over digits) and in the output.  RS_THREADS == RS_BINS: thread d owns digit d.
+    {
+        const int d = threadIdx.x;
+        unsigned tot = 0;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) {
-            unsigned c = cnt[ww][d];
-            cnt[ww][d] = run;
-            run += c;
+            const unsigned c = cnt[ww][d];
+            cnt[ww][d] = tot;                      // warp offset inside the digit's run
+            tot += c;
         }
+        unsigned incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[w] = incl;
+        __syncthreads();
+        unsigned before = 0;
+        for (int ww = 0; ww < w; ww++) before += warp_tot[ww];
+        local_excl[d] = before + incl - tot;
+        gbase[d] = bin_base[d] + hist[(size_t)d * ntiles + blockIdx.x];
     }
     __syncthreads();
 
+    // Stage the tile in digit order in shared memory, then write it out: consecutive staged
+    // entries of one digit go to consecutive addresses, so every digit's run leaves as one
+    // segment instead of 8 + 4 byte stores scattered over 256 destinations.
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; it++) {
         const int k = base + it * 32 + lane;
         if (k < n) {
             const unsigned d = (unsigned)(key[it] >> shift) & (RS_BINS - 1);
-            const unsigned dst = cnt[w][d] + rank[it];
-            keys_out[dst] = key[it];
-            idx_out[dst] = val[it];
+            const unsigned lpos = local_excl[d] + cnt[w][d] + rank[it];
+            s_key[lpos] = key[it];
+            s_val[lpos] = val[it];
+        }
+    }
+    __syncthreads();
+    const int tile_n = min(RS_TILE, n - blockIdx.x * RS_TILE);
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        const int sidx = j * RS_THREADS + threadIdx.x;
+        if (sidx < tile_n) {
+            const uint64_t kk = s_key[sidx];
+            const unsigned d = (unsigned)(kk >> shift) & (RS_BINS - 1);
+            const unsigned dst = gbase[d] + ((unsigned)sidx - local_excl[d]);
+            keys_out[dst] = kk;
+            idx_out[dst] = s_val[sidx];
         }
     }
 }
