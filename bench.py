@@ -47,7 +47,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--n-gas", type=int, default=None, help="override particle count")
-    ap.add_argument("--sequential", action="store_true", help="TG_WVT_SEQUENTIAL")
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact", "sequential"],
+                    help="fast: TG_FAST (FP32 kernel arithmetic, 1e-5 distribution parity); exact: the "
+                         "reference's mixed precision (rho/hsml bit-identical); sequential: "
+                         "TG_WVT_SEQUENTIAL (everything bit-identical)")
+    ap.add_argument("--sequential", action="store_true", help="same as --mode sequential")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--full-relaxation", action="store_true",
@@ -211,7 +215,9 @@ def main():
     torch.cuda.set_stream(stream)           # events below see exactly its kernels
 
     w = workloads.make(args.workload, n_gas=n_gas)          # same seed on every rank
-    flags = tc.WVT_SEQUENTIAL if args.sequential else 0
+    mode = "sequential" if args.sequential else args.mode
+    flags = {"fast": tc.FAST, "exact": 0, "sequential": tc.WVT_SEQUENTIAL}[mode]
+    config["mode"] = mode
     g = tc.HotPath.from_workload(w, device=local_rank, flags=flags, rank=rank, nranks=world,
                                  stream=stream.cuda_stream)
     n = w.n_gas
@@ -363,7 +369,8 @@ def main():
     line = {"metric": "wvt_relax_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 predicate / f64 sums (reference's mixed precision)",
+            "dtype": ("f32 (TG_FAST: exact f32 neighbour predicate, packed-f32 kernels, f64 reduction across lanes)"
+                      if mode == "fast" else "f32 predicate / f64 sums (reference's mixed precision)"),
             "data": "synthetic", "config": config,
             "interactions_per_s": pair_evals / args.steps * value,
             "pair_evals_per_particle": pair_evals / args.steps / n,

@@ -52,6 +52,17 @@ enum {
                                  bit for bit.  With this flag every search returns the exact
                                  predicate set (== Find_ngb_simple, wvt_relax.c:296-340) */
 
+#define TG_FAST 4u             /* FP32 kernel arithmetic in the warm-start sweep (tile_fast.cuh):
+                                 neighbour sets, the frozen-list rule and the control flow of
+                                 Find_hsml stay exactly the reference's; r, u = r/h and the WC6
+                                 polynomials are evaluated in float (packed FP32), sums are
+                                 float per lane and FP64 across lanes.  rho, hsml, VarHsmlFac and
+                                 the displacement then agree with the reference to ~1e-7 except
+                                 where a convergence decision (sph.c:161) flips within that
+                                 noise: <= 5e-5 for ~1e-4 of the particles (north_star asks for
+                                 1e-5 per iteration as a distribution).  Excludes
+                                 TG_WVT_SEQUENTIAL. */
+
 /* One row of the table Global_density_model() walks (wvt_relax.c:227-256):
  * Halo[i].{D_CoM, Rho0, Beta, Rcore, Rcut, Have_Cuspy, Mass[0]} (globals.h:128-157). */
 typedef struct {

@@ -28,6 +28,7 @@ NGBMAX = 2360      # globals.h:50
 NUMITER = 64       # wvt_relax.c:7
 
 WVT_SEQUENTIAL = 1  # tg_config.flags
+FAST = 4  # tg_config.flags: FP32 kernel arithmetic in the warm sweep (tile_fast.cuh)
 EXACT_NEIGHBOURS = 2  # tg_config.flags: exact predicate sets, not the reference tree's (include/toygpu.h)
 
 

@@ -139,9 +139,12 @@ k_reorder_model(int n, const int *__restrict__ idx, const float4 *__restrict__ p
         }
         cube = (double)__fmul_rn(__fmul_rn(hw, hw), hw);   // p3() on the float, wvt_relax.c:117
     }
-    else if (k < (int)(((size_t)n + 7) & ~(size_t)7)) {      // pad: never within reach of anything
+    else if (k < (int)(((size_t)n + 7) & ~(size_t)7)) {
+        // pad of the last run of 8: NaN compares false against every radius, with or without the
+        // periodic wrap of phase 1 (a large finite pad wraps to 0 when Boxsize is a power of two)
         const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
-        soa[k] = 1e18f; soa[n8 + k] = 1e18f; soa[2 * n8 + k] = 1e18f;
+        const float qnan = __int_as_float(0x7fc00000);
+        soa[k] = qnan; soa[n8 + k] = qnan; soa[2 * n8 + k] = qnan;
     }
     const double s = block_sum(cube, sm);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;

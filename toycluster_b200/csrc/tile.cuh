@@ -248,7 +248,7 @@ k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw, const float *__restric
 // at once (the target's coordinate is the scalar operand).  The periodic wrap is
 // d - Boxsize * rint(d / Boxsize) by the 1.5*2^23 trick, which differs from the reference's
 // only for |d| within 1e-7 of Boxsize/2 -- where it changes d^2 by less than the inflation.
-template <bool INTERIOR>
+template <bool INTERIOR, int WARPS = TL_WARPS>
 static __device__ __forceinline__ void tile_phase1(const float *__restrict__ sx, const float *__restrict__ sy,
                                                    const float *__restrict__ sz, const int *s_run,
                                                    unsigned *s_mask, int w, int lane, int ng, int nruns,
@@ -259,7 +259,7 @@ static __device__ __forceinline__ void tile_phase1(const float *__restrict__ sx,
     const float ibox = 1.f / box;
     const f32x2 ib2 = pack2(ibox, ibox), mg2 = pack2(12582912.f, 12582912.f);
     const f32x2 nb2 = pack2(-box, -box);
-    for (int q = w; q < ng; q += TL_WARPS) {
+    for (int q = w; q < ng; q += WARPS) {
         unsigned word = 0;
 #pragma unroll 1
         for (int c = 0; c < 4; c++) {            // four runs of 8 candidates per word

@@ -1,0 +1,400 @@
+// tile_fast.cuh -- TG_FAST: the tile sweep with FP32 kernel arithmetic.
+//
+// The exact modes (tile.cuh, sph.cuh) replay the reference's mixed precision operation for
+// operation: FP64 separations, W and W' as FP64 polynomial chains rounded to float, FP64 sums.
+// ncu showed what that costs on B200: 8.3 k warp instructions per target, a third of them on
+// the FP64 / conversion pipes, and the sweep is issue bound (profiles/r01_final_*).  The
+// north-star tolerance for rho, hsml and the displacement is 1e-5, not bit equality, so this
+// mode keeps everything that DECIDES something exactly as the reference has it and evaluates
+// the smooth parts in float:
+//
+//   kept exact   the neighbour SETS: float, FMA-free predicate of tree.c:67-88 against Hsml,
+//                1.23*Hsml and the WVT radius, displaced-node open tests (defect.cuh), the
+//                frozen list of sph.c:40,56, the outer retry loop (sph.c:36-64), the Newton /
+//                bisection control flow of sph.c:156-195 in FP64 on FP64 totals.
+//   float        r = sqrt(r2) from the predicate's own float r2 (one Newton step on MUFU.RSQ:
+//                ~1 ulp) instead of an FP64 sqrt of FP64 differences; u = r * (1/h);
+//                w(u) = (1-u)^8 (1+8u+25u^2+32u^3) and v(u) = u^2 (1-u)^7 (16u^2+7u+1) as
+//                packed FP32 polynomials (FMUL2/FFMA2, two list entries per instruction),
+//                per-lane float partial sums, FP64 tree over the lanes.
+//   algebra      the sums are dimensionless (sph.c:149-153 with the constants taken out):
+//                  wkNgb = 4pi/3 * kW * Sw,  rho = m kW/h^3 * Sw,
+//                  dRho/dh = -m kW/h^4 (3 Sw - 22 Sv)   =>   omega = 22 Sv / (3 Sw),
+//                so one Find_hsml iteration needs no per-entry h^3, h^4 factors and one FP64
+//                divide.
+//   displacement evaluated in place while the hit is classified (same r2, same gather):
+//                u = r / (0.5 (h_i + h_j) Boxsize), clamped to 1 (the skip of
+//                wvt_relax.c:160 is where W = 0), addend = step h_i W / r * d in float.
+//
+// Per-value error ~1e-7 (u) amplified by |W'/W(0)| <= 2.75: ~3e-7 W(0) per entry, random
+// over ~400 entries => ~1e-7 on the sums, ~3e-8 on hsml per Newton step.  What can differ
+// from the reference by more is a DECISION taken within that noise of its threshold
+// (|wkNgb - 295| < 0.05, sph.c:161): one more or one fewer Newton step, i.e. up to the
+// reference's own convergence slack of ~5e-5 in hsml, for ~1e-4 of the particles.
+// tests/test_gpu_fast.py states this as a distribution against the compiled reference.
+//
+// Everything outside the envelope (cold start, list overflow, a third search, no convergence
+// on the frozen list) goes to the same work list as in tile.cuh and is redone by the exact
+// generic sweep.
+#pragma once
+#include "tile.cuh"
+
+#ifndef TF_WARPS
+#define TF_WARPS 8
+#endif
+#ifndef TF_BLOCKS
+#define TF_BLOCKS 4
+#endif
+
+// Shared memory: bit matrix, run list, per warp a 16-bit hit list and a float separation list.
+#define TF_OFF_MASK 0
+#define TF_OFF_RUN (TF_OFF_MASK + TL_WORDS * TL_MSTRIDE * 4)
+#define TF_OFF_UL (TF_OFF_RUN + TL_RUNS * 4)
+#define TF_OFF_RL (TF_OFF_UL + TF_WARPS * TL_CAP * 2)
+#define TF_OFF_MISC (TF_OFF_RL + TF_WARPS * TL_CAP * 4)
+#define TF_SMEM (TF_OFF_MISC + 64)
+
+#define TF_KW (1365.0 / (64 * K_PI))
+
+// sph.c:80-214 on the frozen float list r[0 .. cnt).  Same control flow as find_hsml
+// (sph.cuh); the per-entry arithmetic is the packed FP32 evaluation described above.
+static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const float *r, int cnt,
+                                                      float &h_io, float &rho_out, float &drho_out,
+                                                      unsigned long long &evals, unsigned &iters)
+{
+    const int lane = lane_id();
+    const double mpart = a.bx.mpart;
+
+    double upper = (double)h_io * K_SQRT3, lower = 0;
+    double hs = h_io, Sw = 0, Sv = 0, c1 = 0;
+    int it = 0;
+    bool done = false;
+
+    const f32x2 one2 = pack2(1.f, 1.f);
+    const f32x2 c32 = pack2(32.f, 32.f), c25 = pack2(25.f, 25.f), c8 = pack2(8.f, 8.f);
+    const f32x2 c16 = pack2(16.f, 16.f), c7 = pack2(7.f, 7.f);
+
+    for (;;) {
+        const float hf = (float)hs;
+        const float inv = __frcp_rn(hf);
+        const f32x2 inv2 = pack2(inv, inv);
+        f32x2 sw2 = pack2(0.f, 0.f), sv2 = pack2(0.f, 0.f);
+        it++;
+
+        auto pair = [&](float r0, float r1) {
+            float u0, u1;
+            unpack2(mul2(pack2(r0, r1), inv2), u0, u1);
+            // r > hs contributes nothing (sph.c:135); clamping u is exact: w(1) = v(1) = 0
+            const f32x2 u = pack2(fminf(u0, 1.f), fminf(u1, 1.f));
+            const f32x2 t = sub2(one2, u);
+            const f32x2 t2 = mul2(t, t), t3 = mul2(t2, t), t4 = mul2(t2, t2);
+            const f32x2 t7 = mul2(t4, t3), t8 = mul2(t7, t);
+            const f32x2 P = fma2(fma2(fma2(c32, u, c25), u, c8), u, one2);
+            const f32x2 Q = fma2(fma2(c16, u, c7), u, one2);
+            sw2 = fma2(t8, P, sw2);
+            sv2 = fma2(mul2(u, u), mul2(t7, Q), sv2);
+        };
+        int k = lane;
+        for (; k + 32 < cnt; k += 64) pair(r[k], r[k + 32]);
+        if (k < cnt) pair(r[k], 3.0e38f);                 // second half: u clamps to 1, adds 0
+        float w0, w1, v0, v1;
+        unpack2(sw2, w0, w1);
+        unpack2(sv2, v0, v1);
+        Sw = warp_sum((double)w0 + (double)w1);
+        Sv = warp_sum((double)v0 + (double)v1);
+        evals += cnt;
+
+        // sph.c:149 with the reference's own factors: the kernels see the float h, p3(hsml) is
+        // the double -- their ratio (1 +- 3e-7) is part of what the iteration converges on
+        const float h3f = __fmul_rn(__fmul_rn(hf, hf), hf);
+        c1 = TF_KW / (double)h3f;
+        const double wkNgb = K_FOURPITHIRD * (hs * hs * hs) * c1 * Sw;
+
+        if (it > 128) break;                                            // sph.c:156
+        const double dev = fabs(wkNgb - TG_DESNNGB);
+        if (dev < 0.05) { done = true; break; }                         // sph.c:161
+        if (fabs(upper - lower) < 1e-4) { hs *= 1.26; break; }          // sph.c:168
+        if (dev < 0.5 * TG_DESNNGB) {                                   // Newton-Raphson
+            // omega = 1 + dRhodHsml * hs / (3 rho) = 22 Sv / (3 Sw)  (m, c1 and hs cancel)
+            // fac = 1 - (wkNgb - 295) / (3 wkNgb omega)
+            double fac = 1 - (wkNgb - TG_DESNNGB) * Sw / (wkNgb * 22.0 * Sv);
+            fac = fmin(1.24, fac);
+            fac = fmax(1 / 1.24, fac);
+            hs *= fac;
+        } else {                                                        // bisection in h^3
+            if (wkNgb > TG_DESNNGB) upper = hs;
+            if (wkNgb < TG_DESNNGB) lower = hs;
+            hs = pow(0.5 * (lower * lower * lower + upper * upper * upper), 1.0 / 3.0);
+        }
+    }
+    iters += it;
+
+    h_io = (float)hs;
+    if (done) {                                                         // sph.c:151-153, 202-210
+        const double rho = mpart * c1 * Sw;
+        const double drho = -mpart * c1 * (3.0 * Sw - 22.0 * Sv) / hs;
+        rho_out = (float)rho;
+        drho_out = (float)drho;
+        const float w0 = (float)c1;                                     // sph_kernel_WC6(0, hsml)
+        const double bias = a.bias_const * mpart * (double)w0;
+        rho_out = (float)((double)rho_out + bias);
+    }
+    return done;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(const SweepArgs a, int tile_lo,
+                                                                        int tile_hi)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned *s_mask = (unsigned *)(smem + TF_OFF_MASK);
+    int *s_run = (int *)(smem + TF_OFF_RUN);        // first particle of each candidate run
+    int *s_misc = (int *)(smem + TF_OFF_MISC);       // [0] tile, [1] next target
+
+    const int lane = lane_id();
+    const int w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1;
+    unsigned short *ul = (unsigned short *)(smem + TF_OFF_UL) + w * TL_CAP;
+    float *rl = (float *)(smem + TF_OFF_RL) + w * TL_CAP;
+
+    const float norm = (float)pow(TG_DESNNGB / *a.vsum / K_FOURPITHIRD, 1.0 / 3.0);   // wvt_relax.c:120
+    const float box = a.bx.box_f, boxhalf = a.bx.boxhalf_f;
+    const float cn = 0.5f * norm * box;              // pair h in length units: (w_i + w_j) * cn
+    const int n = a.t.n;
+
+    unsigned long long c_evals = 0, c_gath = 0, c_pairs = 0;
+    unsigned c_search = 0, c_iters = 0;
+
+    auto hand_back = [&](int i, int why) {     // redo target i on the generic (exact) path
+        if (lane == 0) {
+            a.worklist[atomicAdd(a.nwork, 1)] = i;
+            atomicAdd(&a.counters[4 + why], 1ull);
+        }
+    };
+
+    for (;;) {
+        __syncthreads();              // previous tile fully consumed
+        if (threadIdx.x == 0) { s_misc[0] = atomicAdd(a.next, 1); s_misc[1] = 0; }
+        __syncthreads();
+        const int tile = tile_lo + s_misc[0];
+        if (tile >= tile_hi) break;
+        const int code = a.tile_ng[tile];
+        if (code < 0) {               // whole tile to the generic path
+            if (w == 0) {
+                const int i = tile * 32 + lane;
+                if (i < n) {
+                    a.worklist[atomicAdd(a.nwork, 1)] = i;
+                    atomicAdd(&a.counters[4], 1ull);
+                }
+            }
+            continue;
+        }
+        const int nent = code & 0xfff, nruns = (code >> 12) & 0xffff;
+        const int ng = (nruns + 3) >> 2;           // bit-matrix words
+        const bool interior = (code >> 30) & 1;
+
+        // ---- candidate runs of the tile (ascending) --------------------------------------
+        if (w == 0) {
+            const int *ent = a.tile_groups + (size_t)tile * TL_ENT;
+            int base = 0;
+            for (int e0 = 0; e0 < nent; e0 += 32) {
+                const int e = e0 + lane;
+                const int v = e < nent ? ent[e] : 0;
+                const int c = __popc(v & 0xf);
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(FULL_MASK, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                int off = base + incl - c;
+                for (int b = 0; b < 4; b++)
+                    if (v & (1 << b)) s_run[off++] = (v >> 4) * 32 + 8 * b;
+                base += __shfl_sync(FULL_MASK, incl, 31);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 1: lane = target, superset bit matrix at radius R_i (tile.cuh) --------
+        {
+            const int i = tile * 32 + lane;
+            float xi = 0, yi = 0, zi = 0, R2 = -1.f;
+            if (i < n) {
+                const float4 pi = a.pw[i];
+                xi = pi.x; yi = pi.y; zi = pi.z;
+                const float R = tile_radius(a.hsml_in[i], pi.w, norm, a.bx.box_d);
+                R2 = __fmul_rn(R, R);
+            }
+            const size_t n8 = ((size_t)n + 7) & ~(size_t)7;      // stride of the SoA copy
+            if (interior) tile_phase1<true, TF_WARPS>(a.soa, a.soa + n8, a.soa + 2 * n8, s_run, s_mask, w, lane, ng, nruns, xi, yi, zi, R2, box);
+            else tile_phase1<false, TF_WARPS>(a.soa, a.soa + n8, a.soa + 2 * n8, s_run, s_mask, w, lane, ng, nruns, xi, yi, zi, R2, box);
+        }
+        __syncthreads();
+
+        // ---- phase 2: one warp per target ------------------------------------------------
+        for (;;) {
+            int tsel = 0;
+            if (lane == 0) tsel = atomicAdd(&s_misc[1], 1);
+            tsel = __shfl_sync(FULL_MASK, tsel, 0);
+            if (tsel >= 32) break;
+            const int i = tile * 32 + tsel;
+            if (i >= n) continue;
+
+            float4 pi = a.pw[i];
+            pi.w = fabsf(pi.w);                    // the sign bit is the displaced-node flag
+            const float hA = a.hsml_in[i];
+            const float hB = (float)((double)hA * 1.23);                        // sph.c:51
+            const float hi_w = __fmul_rn(pi.w, norm);                           // wvt_relax.c:124
+            const float hsw = (float)((double)hi_w * a.bx.box_d);               // wvt_relax.c:135
+            const float hA2 = __fmul_rn(hA, hA), hB2 = __fmul_rn(hB, hB), hsw2 = __fmul_rn(hsw, hsw);
+            // wvt_relax.c:167: step * hsml_i * W, W = kW t^8 (...)
+            const float Af = (float)(a.step * (double)hi_w * TF_KW);
+
+            // (1) expand the bit row into a compact candidate-slot list (as in tile.cuh)
+            constexpr int NW = TL_WORDS / 32;
+            unsigned wd[NW];
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < NW; j++) {
+                const int q = j * 32 + lane;
+                wd[j] = q < ng ? s_mask[q * TL_MSTRIDE + tsel] : 0u;
+                c += __popc(wd[j]);
+            }
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int nU = __shfl_sync(FULL_MASK, incl, 31);
+            if (nU > TL_UCAP) { hand_back(i, 1); continue; }
+            {
+                unsigned short *out = ul + (incl - c);
+#pragma unroll
+                for (int j = 0; j < NW; j++) {
+                    if (j * 32 >= ng) break;               // warp-uniform
+                    const unsigned word = wd[j];
+                    const int sbase = (j * 32 + lane) * 32;
+#pragma unroll
+                    for (int b = 0; b < 32; b++)
+                        if (word & (1u << b)) *out++ = (unsigned short)(sbase + b);
+                }
+            }
+            __syncwarp();
+
+            // (2) classify every hit exactly; separation list (A from the front, "1.23*Hsml
+            //     only" from the back); displacement summed in place
+            int cntA = 0, cntBo = 0, cntW = 0;     // cntW: per-lane until reduced below
+            float sx = 0, sy = 0, sz = 0;
+            for (int base = 0; base < nU; base += 32) {
+                const int k = base + lane;
+                const bool live = k < nU;
+                const int slot = live ? ul[k] : 0;
+                const int gidx = s_run[slot >> 3] + (slot & 7);
+                const float4 pj = a.pw[gidx];
+                const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
+                float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+                if (!interior) {       // interior tile: no hit can be a periodic image
+                    if (ax > boxhalf) ax = __fsub_rn(ax, box);
+                    if (ay > boxhalf) ay = __fsub_rn(ay, box);
+                    if (az > boxhalf) az = __fsub_rn(az, box);
+                }
+                const float r2 = sq3_nofma(ax, ay, az);                          // tree.c:88
+                bool inA = live && r2 < hA2, inB = live && r2 < hB2, inW = live && r2 < hsw2;
+                if ((inB | inW) && df_flagged(pj.w)) {
+                    const float4 *path = a.dnodes + a.dmap[gidx];
+                    if (inA) inA = defect_open(path, pi.x, pi.y, pi.z, hA, box, boxhalf);
+                    if (inB) inB = inA || defect_open(path, pi.x, pi.y, pi.z, hB, box, boxhalf);
+                    if (inW) inW = defect_open(path, pi.x, pi.y, pi.z, hsw, box, boxhalf);
+                }
+                // r = sqrt(r2): MUFU.RSQ and one Newton step (r2 = 0 is the target itself)
+                const float y = rsqrtf(r2);
+                float r = r2 * y;
+                r = fmaf(0.5f * y, fmaf(-r, r, r2), r);
+                r = r2 > 0.f ? r : 0.f;
+                if (MODE & MODE_DENSITY) {
+                    const unsigned mA = __ballot_sync(FULL_MASK, inA);
+                    const unsigned mBo = __ballot_sync(FULL_MASK, inB) & ~mA;
+                    if (inA) rl[cntA + __popc(mA & lt)] = r;
+                    else if (inB) rl[TL_CAP - 1 - (cntBo + __popc(mBo & lt))] = r;
+                    cntA += __popc(mA);
+                    cntBo += __popc(mBo);
+                }
+                cntW += inW;
+                if (MODE & MODE_WVT) {
+                    // wvt_relax.c:137-170; nU <= TL_CAP < NGBMAX: the list cut cannot bite
+                    const float hp = (pi.w + fabsf(pj.w)) * cn;                   // :158, length units
+                    const float u = fminf(__fdividef(r, hp), 1.f);                // :160 skip <=> W = 0
+                    const float t = 1.f - u, t2 = t * t, t4 = t2 * t2;
+                    const float P = fmaf(fmaf(fmaf(32.f, u, 25.f), u, 8.f), u, 1.f);
+                    const bool use = inW && gidx != i && r2 > 0.f;               // :141
+                    const float f = use ? Af * (t4 * t4) * P * y : 0.f;
+                    // signed closest-image separation: sign(d) * (|d| [- Boxsize])
+                    sx = fmaf(f, copysignf(1.f, dx) * ax, sx);
+                    sy = fmaf(f, copysignf(1.f, dy) * ay, sy);
+                    sz = fmaf(f, copysignf(1.f, dz) * az, sz);
+                    c_pairs += use && u < 1.f;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cntW += __shfl_xor_sync(FULL_MASK, cntW, o);
+            __syncwarp();
+
+            float h = hA, rho = 0, drho = 0;
+            int cnt = 0;
+            if (MODE & MODE_DENSITY) {
+                // (3) the outer loop of sph.c:36-64, as far as the two prepared radii carry it
+                bool ok = true;
+                if (cntA >= TG_DESNNGB) {                    // first search succeeds: Hsml list
+                    cnt = cntA; h = hA; c_search += 1;
+                } else if (cntA + cntBo >= TG_DESNNGB) {     // second search, 1.23*Hsml
+                    // bring the entries beyond Hsml next to the others (ascending: a write never
+                    // lands on an entry that is still to be read)
+                    const int src0 = TL_CAP - cntBo;
+                    for (int b = 0; b < cntBo; b += 32) {
+                        const int q = b + lane;
+                        const float v = q < cntBo ? rl[src0 + q] : 0.f;
+                        __syncwarp();
+                        if (q < cntBo) rl[cntA + q] = v;
+                        __syncwarp();
+                    }
+                    cnt = cntA + cntBo; h = hB; c_search += 2;
+                } else ok = false;                           // a third search: generic path
+                int why = 3;
+                if (ok) {
+                    __syncwarp();
+                    ok = find_hsml_fast(a, rl, cnt, h, rho, drho, c_evals, c_iters);
+                    why = 4;                                 // no convergence on the frozen list
+                }
+                if (!ok) { hand_back(i, why); continue; }
+            }
+            c_search += (MODE & MODE_WVT) ? 1 : 0;
+            c_gath += max(cnt, cntW);
+
+            // (4) results
+            double dsx = 0, dsy = 0, dsz = 0;
+            if (MODE & MODE_WVT) { dsx = warp_sum((double)sx); dsy = warp_sum((double)sy); dsz = warp_sum((double)sz); }
+            if (lane == 0) {
+                if (MODE & MODE_DENSITY) {                                       // sph.c:66-70
+                    const float q = __fmul_rn(__fdiv_rn(h, __fmul_rn(3.f, rho)), drho);
+                    a.hsml_out[i] = h;
+                    a.rho_out[i] = rho;
+                    a.varh_out[i] = (float)(1.0 / (double)__fadd_rn(1.f, q));
+                }
+                if (MODE & MODE_WVT) {
+                    a.delta[i] = (float)dsx;
+                    a.delta[n + i] = (float)dsy;
+                    a.delta[2 * (size_t)n + i] = (float)dsz;
+                }
+            }
+        }
+    }
+
+    const unsigned long long pairs = warp_sum_u64(c_pairs);
+    if (lane == 0) {
+        atomicAdd(&a.counters[0], c_evals + pairs);
+        atomicAdd(&a.counters[1], c_gath);
+        atomicAdd(&a.counters[2], (unsigned long long)c_search);
+        atomicAdd(&a.counters[3], (unsigned long long)c_iters);
+    }
+}

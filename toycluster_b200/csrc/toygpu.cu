@@ -31,6 +31,7 @@
 #include "guess.cuh"
 #include "sph.cuh"
 #include "tile.cuh"
+#include "tile_fast.cuh"
 #include "bfield.cuh"
 
 static thread_local std::string g_create_error;
@@ -98,7 +99,7 @@ struct tg_ctx {
     double *gscratch = nullptr;
     int sweep_blocks = 0;
     int *tile_ng = nullptr, *tile_groups = nullptr, *worklist = nullptr;
-    int tile_blocks = 0;
+    int tile_blocks = 0, fast_blocks = 0;
     bool use_tiles = true;
 
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -172,6 +173,8 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     *out = nullptr;
     if (cfg->n_gas <= 0 || !(cfg->boxsize > 0) || !(cfg->mpart_gas > 0))
         return fail(c, TG_EINVAL, "tg_create: n_gas, boxsize and mpart_gas must be positive");
+    if ((cfg->flags & TG_FAST) && (cfg->flags & TG_WVT_SEQUENTIAL))
+        return fail(c, TG_EINVAL, "tg_create: TG_FAST and TG_WVT_SEQUENTIAL exclude each other");
     const int nranks = cfg->nranks > 0 ? cfg->nranks : 1;
     if (cfg->rank < 0 || cfg->rank >= nranks)
         return fail(c, TG_EINVAL, "tg_create: rank %d outside [0,%d)", cfg->rank, nranks);
@@ -335,6 +338,18 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
                                                           TL_WARPS * 32, TL_SMEM));
         if (tile_per_sm < 1) tile_per_sm = 1;
         c->tile_blocks = prop.multiProcessorCount * tile_per_sm;
+    }
+    {
+        auto set = [&](const void *f) {
+            return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
+        };
+        CUC(set((const void *)k_sweep_tile_fast<MODE_DENSITY>));
+        CUC(set((const void *)k_sweep_tile_fast<MODE_DENSITY | MODE_WVT>));
+        int per = 1;
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_sweep_tile_fast<MODE_DENSITY | MODE_WVT>,
+                                                          TF_WARPS * 32, TF_SMEM));
+        if (per < 1) per = 1;
+        c->fast_blocks = prop.multiProcessorCount * per;
     }
     CUC(dmalloc(&c->tile_ng, (size_t)t.lvl_n[0]));
     CUC(dmalloc(&c->tile_groups, (size_t)t.lvl_n[0] * TL_ENT));
@@ -660,7 +675,15 @@ template <int MODE> static int launch_tiled(tg_ctx *c, SweepArgs a)
         c->bvh, c->box, c->pw, c->hsml_in, c->scal, tile_lo, tile_hi, c->tile_ng, c->tile_groups);
     LAUNCH_CHECK();
     a.next = c->flags;
-    k_sweep_tile<MODE><<<c->tile_blocks, TL_WARPS * 32, TL_SMEM, c->stream>>>(a, tile_lo, tile_hi);
+    constexpr bool has_fast = MODE == MODE_DENSITY || MODE == (MODE_DENSITY | MODE_WVT);
+    bool fast = false;
+    if constexpr (has_fast) fast = (c->cfg.flags & TG_FAST) != 0;
+    if (fast) {
+        if constexpr (has_fast)
+            k_sweep_tile_fast<MODE><<<c->fast_blocks, TF_WARPS * 32, TF_SMEM, c->stream>>>(a, tile_lo, tile_hi);
+    } else {
+        k_sweep_tile<MODE><<<c->tile_blocks, TL_WARPS * 32, TL_SMEM, c->stream>>>(a, tile_lo, tile_hi);
+    }
     LAUNCH_CHECK();
     a.next = c->flags + 6;
     k_sweep<MODE, true><<<c->sweep_blocks, SW_WARPS * 32, smem, c->stream>>>(a);
