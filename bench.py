@@ -129,14 +129,27 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- reference arm
 
-def run_reference(workload_name, n_target, steps, warmup):
-    """The reference's own CPU code (oracle/_ref) on a bounded sample, all host threads."""
+def run_reference(workload_name, n_target, steps, warmup, full_size):
+    """The reference's own CPU code (oracle/_ref: the unmodified sources), all host threads.
+
+    full_size (the --impl reference arm): the TRUE workload -- same N_gas as our arm.  A 10 M
+    iteration of the reference costs ~40 s on 16 cores (the cold first one ~100 s), so the arm
+    is bounded by the number of iterations, never by shrinking the problem: one cold + one warm
+    iteration as warm-up, then min(steps, 2) timed steady-state iterations; the printed line
+    says how many were timed.
+    not full_size (the cpu_baseline leg inside our own arm, ~10-30 s of CPU work): the same
+    merger model at N_gas = CPU_SAMPLE_N, steps/s scaled by N -- marked `scaled`."""
     from toycluster_b200 import workloads
     from oracle import ref
     if not ref.available():
         return None
     cores = os.cpu_count() or 1
-    n = CPU_SAMPLE_N if n_target > CPU_SAMPLE_N else n_target
+    if full_size:
+        n = n_target
+        warmup = min(warmup, 2) if n > 2_000_000 else warmup
+        steps = min(steps, 2) if n > 2_000_000 else (min(steps, 5) if n > 300_000 else steps)
+    else:
+        n = CPU_SAMPLE_N if n_target > CPU_SAMPLE_N else n_target
     n = max(n, 256 * cores)                       # wvt_relax.c:127 chunk must stay >= 1
     w = workloads.make(workload_name, n_gas=n)
     r = ref.Ref(w.n_gas, w.boxsize, w.mpart_gas, w.mtotal, w.halo_table(), cores)
@@ -152,11 +165,14 @@ def run_reference(workload_name, n_target, steps, warmup):
     # stamps[k] = start of iteration k; iteration k spans stamps[k]..stamps[k+1]
     dt = np.diff(np.array(stamps))[warmup:warmup + steps]
     s_per_step = float(dt.mean())
-    return dict(n_sample=n, cores=r.nthreads, s_per_step_sample=s_per_step,
-                steps_per_s_scaled=(n / n_target) / s_per_step,
-                sample=(f"{workload_name} model at N_gas={n}, {steps} steady-state WVT iterations "
-                        f"after {warmup} warm-up (unmodified reference sources, oracle/_ref), "
-                        f"steps/s scaled by N_gas/{n_target} (cost per particle taken as constant)"))
+    scaled = n != n_target
+    return dict(n_sample=n, cores=r.nthreads, s_per_step_sample=s_per_step, steps=len(dt), warmup=warmup,
+                scaled=scaled, steps_per_s=(n / n_target) / s_per_step,
+                sample=(f"{workload_name} at N_gas={n}" + ("" if not scaled else f" (target {n_target})") +
+                        f", {len(dt)} steady-state WVT iterations after {warmup} warm-up (the first one cold); "
+                        "unmodified reference sources (oracle/_ref)" +
+                        (f"; steps/s scaled by N_gas/{n_target} (cost per particle taken as constant)"
+                         if scaled else "; full size, nothing scaled")))
 
 
 # --------------------------------------------------------------------------- our arm
@@ -176,13 +192,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        res = run_reference(args.workload, n_gas, args.steps, args.warmup)
+        res = run_reference(args.workload, n_gas, args.steps, args.warmup, full_size=True)
         if res is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libtoyref.so not built"}))
             return
-        v = res["steps_per_s_scaled"]
+        v = res["steps_per_s"]
+        config["n_gas_timed"] = res["n_sample"]
+        config["scaled"] = res["scaled"]
         line = {"metric": "wvt_relax_steps_per_s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v,
+                "steps": res["steps"], "warmup": res["warmup"], "steps_requested": args.steps,
+                "warmup_requested": args.warmup, "ms_per_step": 1e3 / v,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64",
                 "data": "synthetic", "config": config, "impl": "reference",
                 "cpu_baseline": {"value": v, "unit": "steps/s", "cores": res["cores"],
@@ -221,33 +240,29 @@ def main():
     g = tc.HotPath.from_workload(w, device=local_rank, flags=flags, rank=rank, nranks=world,
                                  stream=stream.cuda_stream)
     n = w.n_gas
-    ex = g.exchange()
-    chunk, npad = ex.chunk, ex.chunk * world
-
-    class _Dev:     # wrap library-owned device memory as a torch tensor (zero copy)
-        def __init__(self, ptr, nbytes):
-            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1",
-                                             "data": (ptr, False), "version": 2}
-
-    posh_full = torch.as_tensor(_Dev(ex.pos_hsml_dev, npad * 16), device="cuda").view(torch.float32)
+    if world > 1:
+        # the collectives of a step (all-gather of the moved slices, reduction of the error
+        # statistics) run INSIDE libtoygpu.so on its own NCCL communicator; torch.distributed
+        # only carries the 128-byte id to the other ranks and the timing reductions below
+        ident = [tc.HotPath.comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            g.comm_init(ident[0])
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if n * 16 <= L2_BYTES else None
-
-    from toycluster_b200.dist import allgather_slices
-
-    def exchange():
-        allgather_slices(posh_full, rank, chunk, 4)     # one in-place NCCL all-gather per step
 
     def one_step(step):
         if flush is not None:
             flush.zero_()
-        g.wvt_iteration(step)
-        exchange()
+        g.wvt_iteration(step)          # sort, index, sweep, error statistics, move, exchange
         return g.stats()
 
-    # pinned host state for the e2e leg
-    pos_host = torch.from_numpy(w.pos).pin_memory()
-    hsml_host = torch.zeros(n, dtype=torch.float32).pin_memory()
-    pos_np, hsml_np = pos_host.numpy(), hsml_host.numpy()
     pos_np0 = w.pos.copy()
 
     def sync_all():
@@ -257,14 +272,15 @@ def main():
             torch.cuda.synchronize()
 
     # ---- resident-in-HBM timing -------------------------------------------------------
-    g.upload(pos_np)
+    g.upload(pos_np0)
     step = STEP0
     for _ in range(args.warmup):
         one_step(step)
     sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    acc = dict(pair_evals=0, gathered=0, kernels=0, sweep_ms=0.0, step_ms=0.0)
+    acc = dict(pair_evals=0, gathered=0, kernels=0, sweep_ms=0.0, step_ms=0.0, searches=0, hsml_iters=0,
+               handed_back=0)
     t_wall = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
@@ -278,8 +294,8 @@ def main():
     ms_total = e0.elapsed_time(e1)
 
     red = torch.tensor([ms_total, t_wall * 1e3, acc["sweep_ms"]], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(acc["pair_evals"]), float(acc["gathered"])], dtype=torch.float64,
-                       device="cuda")
+    tot = torch.tensor([float(acc["pair_evals"]), float(acc["gathered"]), float(acc["searches"]),
+                        float(acc["hsml_iters"]), float(acc["handed_back"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -292,54 +308,51 @@ def main():
     else:
         per_rank = per_rank[None]
     ms_total, wall_ms, sweep_ms_max = red.tolist()
-    pair_evals, gathered = tot.tolist()
+    pair_evals, gathered, searches, hsml_iters, handed = tot.tolist()
 
-    # ---- end to end through the C ABI with host buffers --------------------------------
+    # ---- end to end through the operator boundary the C driver uses (main.c:52) ----------
+    # Regularise_sph_particles() == tg_upload(AoS ParticleData 64 B + GasParticleData 60 B) ->
+    # tg_regularise -> tg_download(AoS): the records live in page-locked HOST memory (as the shim
+    # pins the driver's P / SphP), cross the bus whole in both directions inside the timed
+    # region, and are unpacked / permuted / patched on the device.  One call runs `steps`
+    # iterations, so the marshalling is amortised exactly as it is in the real program.
     e2e = None
     if not args.no_e2e:
         out = g.download()
-        pos_np[:] = out["pos"]
-        hsml_np[:] = out["hsml"]
+        Pdt = np.dtype([("Pos", "3f4"), ("Vel", "3f4"), ("ID", "i4"), ("Type", "i4"),
+                        ("Key", "2u8"), ("Tree_Parent", "i4"), ("pad", "3i4")])           # globals.h:161-168
+        Sdt = np.dtype([("U", "f4"), ("Rho", "f4"), ("Hsml", "f4"), ("VarHsmlFac", "f4"),
+                        ("Bfld", "3f4"), ("Apot", "3f4"), ("ID", "f4"), ("Rho_Model", "f4"),
+                        ("Rs", "3f4")])                                                   # globals.h:170-180
+        assert Pdt.itemsize == 64 and Sdt.itemsize == 60
+        P = torch.zeros(n * 64, dtype=torch.uint8).pin_memory().numpy().view(Pdt)
+        S = torch.zeros(n * 60, dtype=torch.uint8).pin_memory().numpy().view(Sdt)
+        P["Pos"], P["ID"] = out["pos"], np.arange(n)
+        S["Hsml"] = out["hsml"]                              # warm start: a mid-relaxation call
         sync_all()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            if world == 1:
-                g.upload(pos_np, hsml_np)                    # H2D from pinned memory
-            else:                                            # each rank ships only its slice
-                cold = g.upload_slice(pos_np, hsml_np)
-                exchange()
-                flag = torch.tensor([int(cold)], device="cuda")
-                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-                g.set_cold(bool(flag.item()))
-            g.wvt_iteration(step)
-            exchange()
-            if world == 1:
-                g.lib.tg_download_soa(g._ctx, pos_np.ctypes.data, None, hsml_np.ctypes.data,
-                                      None, None, None, None)   # D2H of the step's result
-            else:
-                torch.cuda.synchronize()
-                g.download_slice(pos_np, hsml_np)            # D2H of this rank's slice
+        g.upload_records(P, S)                               # H2D: 124 B per particle
+        done, _rows = g.regularise_sph_particles(max_iters=args.steps)
+        g.download_records(P, S)                             # D2H: 124 B per particle, permuted
         sync_all()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        final = g.download()                                 # after the exchange every rank holds it all
+        final = g.download()
         checksum = float(final["pos"].astype(np.float64).sum()) + float(final["hsml"].astype(np.float64).sum())
-        e2e = {"value": args.steps / dt.item(), "unit": "steps/s", "state_checksum": checksum,
-               "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,   # summed over ranks
-               "ms_per_step": dt.item() * 1e3 / args.steps}
+        e2e = {"value": done / dt.item(), "unit": "steps/s", "state_checksum": checksum,
+               "call": "tg_upload(AoS 64+60 B) -> tg_regularise -> tg_download(AoS), pinned host records",
+               "iterations_per_call": done,
+               "h2d_bytes_per_step": 124 * n / done, "d2h_bytes_per_step": 124 * n / done,
+               "h2d_bytes_per_call": 124 * n, "d2h_bytes_per_call": 124 * n,
+               "ms_per_step": dt.item() * 1e3 / done, "ms_per_call": dt.item() * 1e3}
 
     full = None
     if args.full_relaxation:
-        from toycluster_b200.dist import regularise as regularise_ranks
         g.upload(pos_np0)
         sync_all()
         t0 = time.perf_counter()
-        if world == 1:
-            iters, rows = g.regularise_sph_particles()
-        else:
-            rows = regularise_ranks(g, exchange, mtotal=w.mtotal, device="cuda")
-            iters = len(rows)
+        iters, rows = g.regularise_sph_particles()
         sync_all()
         full = {"iterations": iters, "seconds": time.perf_counter() - t0,
                 "final_err_mean": rows[-1]["mean"], "final_step": rows[-1]["step"]}
@@ -376,6 +389,9 @@ def main():
             "pair_evals_per_particle": pair_evals / args.steps / n,
             "gathered_per_particle": gathered / args.steps / n,
             "wall_ms_per_step": wall_ms / args.steps,
+            "searches_per_particle": searches / args.steps / n,
+            "hsml_iters_per_particle": hsml_iters / args.steps / n,
+            "handed_back_per_step": handed / args.steps,
             "gpu_launches": int(acc["kernels"]), "clocks": clocks, "roofline": roofline}
     if world > 1:     # per-rank device times: load balance of the target partition
         line["per_rank_ms"] = {"sweep": [round(v, 3) for v in per_rank[:, 0].tolist()],
@@ -385,11 +401,12 @@ def main():
     if full:
         line["full_relaxation"] = full
     if not args.no_cpu_baseline and world == 1:
-        res = run_reference(args.workload, n, 2, 1)
+        res = run_reference(args.workload, n, 2, 1, full_size=False)
         if res:
-            line["cpu_baseline"] = {"value": res["steps_per_s_scaled"], "unit": "steps/s",
+            line["cpu_baseline"] = {"value": res["steps_per_s"], "unit": "steps/s",
                                     "cores": res["cores"], "kind": "reference",
-                                    "sample": res["sample"],
+                                    "sample": res["sample"], "scaled": res["scaled"],
+                                    "n_sample": res["n_sample"],
                                     "s_per_step_sample": res["s_per_step_sample"]}
     print(json.dumps(line))
     if world > 1:

@@ -81,6 +81,10 @@ typedef struct {
     unsigned flags;
     int rank, nranks;    /* target-particle partition; 0,1 for one GPU */
     void *stream;        /* cudaStream_t to run on (e.g. the caller's NCCL stream); NULL = own */
+    int ngpus;           /* > 1: ONE process drives ngpus devices: the context is a
+                            group of rank contexts with their own NCCL communicators; every call
+                            below then acts on all of them (rank/nranks must be 0/0 or 0/1) */
+    const int *devices;  /* ngpus device ordinals, or NULL for 0 .. ngpus-1 */
 } tg_config;
 
 typedef struct tg_ctx tg_ctx;
@@ -117,6 +121,16 @@ int tg_create(tg_ctx **out, const tg_config *cfg);
 int tg_destroy(tg_ctx *ctx);
 const char *tg_last_error(const tg_ctx *ctx);    /* ctx may be NULL (last create error) */
 
+/* One process per GPU (rank / nranks in tg_config): rank 0 obtains a 128-byte NCCL id, the
+ * host ships it to the other ranks by whatever channel it has, every rank joins.  From then on
+ * the library itself exchanges what the ranks need -- the all-gather of the moved (x, y, z,
+ * Hsml) slices, Rho / VarHsmlFac / Bfld, the driver's records, and the reductions of the
+ * error statistics and status flags -- on its own stream, and tg_regularise,
+ * tg_wvt_begin (which then returns GLOBAL sums) and tg_upload / tg_download work as on one
+ * GPU.  tg_upload* read, and tg_download writes, this rank's slice [lo, hi) of the host arrays. */
+int tg_comm_id(unsigned char id128[128]);
+int tg_comm_init(tg_ctx *ctx, const unsigned char id128[128]);
+
 /* Halo table for Global_density_model (replaces reading Halo[] / Param.Nhalos). */
 int tg_set_halos(tg_ctx *ctx, int n, const tg_halo *halos);
 
@@ -125,6 +139,11 @@ int tg_set_halos(tg_ctx *ctx, int n, const tg_halo *halos);
  * Pos at +0) and struct GasParticleData (globals.h:170-180, Hsml at +8, Apot at +28).
  * Only the gas range [0, n_gas) is read. */
 int tg_upload(tg_ctx *ctx, const void *P, size_t p_stride, const void *SphP, size_t s_stride);
+/* Page-lock a host range the caller will pass to tg_upload / tg_download again and again (the
+ * driver's P and SphP live for the whole process, setup.c:244-250) so the copies are plain DMA.
+ * Optional; ranges are released by tg_unpin_host or tg_destroy and must outlive that. */
+int tg_pin_host(tg_ctx *ctx, void *ptr, size_t bytes);
+int tg_unpin_host(tg_ctx *ctx, void *ptr);
 /* Same from plain arrays: pos[n][3]; hsml[n] or NULL (cold start, SphP.Hsml == 0). */
 int tg_upload_soa(tg_ctx *ctx, const float *pos, const float *hsml);
 int tg_set_apot(tg_ctx *ctx, const float *apot /* [n][3], upload order */);

@@ -251,3 +251,39 @@ def test_sort_with_long_runs_of_nearly_equal_keys():
     assert dup >= 2
     assert np.array_equal(perm, want)
     assert np.array_equal(g.download()["pos"], pos[want])
+
+
+def test_records_device_path_is_idempotent_and_pinned():
+    """tg_upload / tg_download keep the driver's records resident on the device: a second
+    download without an upload in between returns the same bytes (the records on the device are
+    already in the new order), with and without page-locked host arrays."""
+    w = workloads.make("merger_1e6", n_gas=30_001)
+    n = w.n_gas
+    Pdt = np.dtype([("Pos", "3f4"), ("Vel", "3f4"), ("ID", "i4"), ("Type", "i4"),
+                    ("Key", "2u8"), ("Tree_Parent", "i4"), ("pad", "3i4")])
+    Sdt = np.dtype([("U", "f4"), ("Rho", "f4"), ("Hsml", "f4"), ("VarHsmlFac", "f4"),
+                    ("Bfld", "3f4"), ("Apot", "3f4"), ("ID", "f4"), ("Rho_Model", "f4"), ("Rs", "3f4")])
+    res = []
+    for pin in (False, True):
+        P, S = np.zeros(n, Pdt), np.zeros(n, Sdt)
+        P["Pos"], P["ID"], S["U"] = w.pos, np.arange(n) * 3 + 1, np.arange(n) * 0.25
+        g = tc.HotPath.from_workload(w)
+        if pin:
+            g.pin_host(P)
+            g.pin_host(S)
+        g.upload_records(P, S)
+        g.wvt_iteration(0.0085)
+        g.wvt_iteration(0.0085)
+        g.download_records(P, S)
+        first = (P.tobytes(), S.tobytes())
+        o = g.download()
+        assert np.array_equal(o["id"], np.arange(n))        # records and state are in the same order now
+        g.download_records(P, S)
+        assert (P.tobytes(), S.tobytes()) == first
+        assert np.array_equal(S["U"], (P["ID"] - 1) / 3 * np.float32(0.25))
+        if pin:
+            g.unpin_host(P)
+            g.unpin_host(S)
+        g.close()
+        res.append(first)
+    assert res[0] == res[1]

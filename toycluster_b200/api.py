@@ -45,7 +45,8 @@ class _Halo(C.Structure):
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int), ("n_gas", C.c_int), ("boxsize", C.c_double),
                 ("mpart_gas", C.c_double), ("mtotal", C.c_double), ("flags", C.c_uint),
-                ("rank", C.c_int), ("nranks", C.c_int), ("stream", C.c_void_p)]
+                ("rank", C.c_int), ("nranks", C.c_int), ("stream", C.c_void_p),
+                ("ngpus", C.c_int), ("devices", C.POINTER(C.c_int))]
 
 
 class _BField(C.Structure):
@@ -82,7 +83,8 @@ EXPORTS = [
     "tg_upload_soa_slice", "tg_set_cold", "tg_download_soa_slice", "tg_set_apot", "tg_download", "tg_download_soa", "tg_find_sph_quantities", "tg_regularise",
     "tg_bfld_from_rotA", "tg_wvt_iteration", "tg_wvt_begin", "tg_wvt_finish", "tg_wvt_scratch", "tg_get_stats", "tg_peano_keys",
     "tg_sort", "tg_find_ngb", "tg_guess_hsml", "tg_get_exchange",
-    "tg_make_magnetic_field", "tg_get_apot",
+    "tg_make_magnetic_field", "tg_get_apot", "tg_pin_host", "tg_unpin_host",
+    "tg_comm_id", "tg_comm_init",
 ]
 
 _lib = None
@@ -141,6 +143,10 @@ def load():
     lib.tg_make_magnetic_field.argtypes = [C.c_void_p, C.POINTER(_BField), C.POINTER(C.c_double),
                                            C.POINTER(C.c_int)]
     lib.tg_get_apot.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tg_pin_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.tg_unpin_host.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tg_comm_id.argtypes = [C.c_void_p]
+    lib.tg_comm_init.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -153,12 +159,14 @@ class HotPath:
     """One device context == the global state the reference's path works on."""
 
     def __init__(self, n_gas, boxsize, mpart_gas, mtotal, halo_table, device=0, flags=0,
-                 rank=0, nranks=1, stream=None):
+                 rank=0, nranks=1, stream=None, ngpus=0, devices=None):
         self.lib = load()
         self.n = int(n_gas)
         self._ctx = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices) if devices else None
         cfg = _Config(int(device), self.n, float(boxsize), float(mpart_gas), float(mtotal),
-                      int(flags), int(rank), int(nranks), C.c_void_p(stream or None))
+                      int(flags), int(rank), int(nranks), C.c_void_p(stream or None),
+                      int(ngpus), devs)
         rc = self.lib.tg_create(C.byref(self._ctx), C.byref(cfg))
         if rc != 0:
             msg = self.lib.tg_last_error(None).decode()
@@ -181,6 +189,20 @@ class HotPath:
         if rc != 0:
             raise ToyGpuError(f"libtoygpu error {rc}: "
                               f"{self.lib.tg_last_error(self._ctx).decode()}")
+
+    # ---- multi-GPU inside the library (one process per GPU) ------------------------------
+    @staticmethod
+    def comm_id() -> bytes:
+        """128-byte NCCL id (rank 0); ship it to the other ranks, then comm_init everywhere."""
+        buf = (C.c_ubyte * 128)()
+        lib = load()
+        if lib.tg_comm_id(buf) != 0:
+            raise ToyGpuError("tg_comm_id: " + lib.tg_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, id128: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(id128)
+        self._check(self.lib.tg_comm_init(self._ctx, buf))
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -227,6 +249,14 @@ class HotPath:
     def download_records(self, P, SphP):
         self._check(self.lib.tg_download(self._ctx, _ptr(P), P.strides[0], _ptr(SphP),
                                          SphP.strides[0]))
+
+    def pin_host(self, arr):
+        """Page-lock a numpy array that will be passed to upload_records / download_records
+        repeatedly (the C driver's P / SphP).  Keep ``arr`` alive until unpin_host / close."""
+        self._check(self.lib.tg_pin_host(self._ctx, _ptr(arr), arr.nbytes))
+
+    def unpin_host(self, arr):
+        self._check(self.lib.tg_unpin_host(self._ctx, _ptr(arr)))
 
     def set_apot(self, apot):
         apot = np.ascontiguousarray(apot, dtype=np.float32)

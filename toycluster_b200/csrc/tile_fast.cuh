@@ -37,36 +37,70 @@
 // on the frozen list) goes to the same work list as in tile.cuh and is redone by the exact
 // generic sweep.
 #pragma once
+#include <type_traits>
 #include "tile.cuh"
 
 #ifndef TF_WARPS
 #define TF_WARPS 8
 #endif
 #ifndef TF_BLOCKS
-#define TF_BLOCKS 4
+#define TF_BLOCKS 3
 #endif
 
-// Shared memory: bit matrix, run list, per warp a 16-bit hit list and a float separation list.
+// Shared memory: bit matrix, run list, per warp a hit list (particle indices) and a float
+// separation list, per-warp statistics.
 #define TF_OFF_MASK 0
 #define TF_OFF_RUN (TF_OFF_MASK + TL_WORDS * TL_MSTRIDE * 4)
 #define TF_OFF_UL (TF_OFF_RUN + TL_RUNS * 4)
-#define TF_OFF_RL (TF_OFF_UL + TF_WARPS * TL_CAP * 2)
+#define TF_OFF_RL (TF_OFF_UL + TF_WARPS * TL_CAP * 4)
 #define TF_OFF_MISC (TF_OFF_RL + TF_WARPS * TL_CAP * 4)
-#define TF_SMEM (TF_OFF_MISC + 64)
+#define TF_OFF_CNT (TF_OFF_MISC + 64)
+#define TF_SMEM (TF_OFF_CNT + TF_WARPS * 32)
 
 #define TF_KW (1365.0 / (64 * K_PI))
 
+static __device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+static __device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Sum of two doubles per lane over the warp with 6 shuffle steps instead of 10: the first
+// step trades one quantity for the other between lane pairs, the last one trades the totals.
+static __device__ __forceinline__ void warp_sum2(double &a, double &b)
+{
+    const bool odd = lane_id() & 1;
+    const double give = odd ? a : b, keep = odd ? b : a;
+    double v = keep + __shfl_xor_sync(FULL_MASK, give, 1);      // even lanes: a, odd lanes: b
+#pragma unroll
+    for (int o = 2; o <= 16; o <<= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    const double other = __shfl_xor_sync(FULL_MASK, v, 1);
+    a = odd ? other : v;
+    b = odd ? v : other;
+}
+
 // sph.c:80-214 on the frozen float list r[0 .. cnt).  Same control flow as find_hsml
 // (sph.cuh); the per-entry arithmetic is the packed FP32 evaluation described above.
+// u = r * inv with inv ~ 1/h from MUFU.RCP; its relative error e (exactly inv*h - 1, one FMA)
+// shifts every u alike, which is a first-order correction of the sum:
+//   Sw(u) = Sw(u (1+e)) - e * sum u w'(u) = Sw(u (1+e)) + 22 e Sv      (u w'(u) = -22 v(u)).
 static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const float *r, int cnt,
                                                       float &h_io, float &rho_out, float &drho_out,
-                                                      unsigned long long &evals, unsigned &iters)
+                                                      unsigned &evals, unsigned &iters)
 {
     const int lane = lane_id();
     const double mpart = a.bx.mpart;
+    const double KN = K_FOURPITHIRD * TF_KW;
 
     double upper = (double)h_io * K_SQRT3, lower = 0;
-    double hs = h_io, Sw = 0, Sv = 0, c1 = 0;
+    double hs = h_io, Sw = 0, Sv = 0;
     int it = 0;
     bool done = false;
 
@@ -76,7 +110,8 @@ static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const 
 
     for (;;) {
         const float hf = (float)hs;
-        const float inv = __frcp_rn(hf);
+        const float inv = rcp_approx(hf);
+        const float einv = fmaf(inv, hf, -1.f);
         const f32x2 inv2 = pack2(inv, inv);
         f32x2 sw2 = pack2(0.f, 0.f), sv2 = pack2(0.f, 0.f);
         it++;
@@ -94,21 +129,24 @@ static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const 
             sw2 = fma2(t8, P, sw2);
             sv2 = fma2(mul2(u, u), mul2(t7, Q), sv2);
         };
-        int k = lane;
-        for (; k + 32 < cnt; k += 64) pair(r[k], r[k + 32]);
-        if (k < cnt) pair(r[k], 3.0e38f);                 // second half: u clamps to 1, adds 0
+        // the caller padded the list to a multiple of 64 with entries far outside (u clamps to 1)
+#pragma unroll 2
+        for (int k = lane; k < cnt; k += 64) pair(r[k], r[k + 32]);
         float w0, w1, v0, v1;
         unpack2(sw2, w0, w1);
         unpack2(sv2, v0, v1);
-        Sw = warp_sum((double)w0 + (double)w1);
-        Sv = warp_sum((double)v0 + (double)v1);
+        Sw = (double)w0 + (double)w1;
+        Sv = (double)v0 + (double)v1;
+        warp_sum2(Sw, Sv);
+        Sw = fma(22.0 * (double)einv, Sv, Sw);
         evals += cnt;
 
         // sph.c:149 with the reference's own factors: the kernels see the float h, p3(hsml) is
-        // the double -- their ratio (1 +- 3e-7) is part of what the iteration converges on
+        // the double -- their ratio hs^3 / (float)h^3 = 1 + g, |g| < 3e-7, is part of what the
+        // iteration converges on.  g = (hs^3 - h3f) / h3f; the float inv^3 is plenty for 1/h3f.
         const float h3f = __fmul_rn(__fmul_rn(hf, hf), hf);
-        c1 = TF_KW / (double)h3f;
-        const double wkNgb = K_FOURPITHIRD * (hs * hs * hs) * c1 * Sw;
+        const double g = (hs * hs * hs - (double)h3f) * (double)(inv * inv * inv);
+        const double wkNgb = fma(KN * Sw, g, KN * Sw);
 
         if (it > 128) break;                                            // sph.c:156
         const double dev = fabs(wkNgb - TG_DESNNGB);
@@ -131,6 +169,8 @@ static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const 
 
     h_io = (float)hs;
     if (done) {                                                         // sph.c:151-153, 202-210
+        const float hf = (float)hs;
+        const double c1 = TF_KW / (double)__fmul_rn(__fmul_rn(hf, hf), hf);
         const double rho = mpart * c1 * Sw;
         const double drho = -mpart * c1 * (3.0 * Sw - 22.0 * Sv) / hs;
         rho_out = (float)rho;
@@ -150,20 +190,19 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
     unsigned *s_mask = (unsigned *)(smem + TF_OFF_MASK);
     int *s_run = (int *)(smem + TF_OFF_RUN);        // first particle of each candidate run
     int *s_misc = (int *)(smem + TF_OFF_MISC);       // [0] tile, [1] next target
+    unsigned long long *s_cnt = (unsigned long long *)(smem + TF_OFF_CNT);   // per warp: evals, gathered, searches, iters
 
     const int lane = lane_id();
     const int w = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1;
-    unsigned short *ul = (unsigned short *)(smem + TF_OFF_UL) + w * TL_CAP;
+    int *ul = (int *)(smem + TF_OFF_UL) + w * TL_CAP;          // hit list: particle indices
     float *rl = (float *)(smem + TF_OFF_RL) + w * TL_CAP;
+    unsigned long long *cw = s_cnt + w * 4;
+    if (lane < 4) cw[lane] = 0;
 
     const float norm = (float)pow(TG_DESNNGB / *a.vsum / K_FOURPITHIRD, 1.0 / 3.0);   // wvt_relax.c:120
     const float box = a.bx.box_f, boxhalf = a.bx.boxhalf_f;
-    const float cn = 0.5f * norm * box;              // pair h in length units: (w_i + w_j) * cn
     const int n = a.t.n;
-
-    unsigned long long c_evals = 0, c_gath = 0, c_pairs = 0;
-    unsigned c_search = 0, c_iters = 0;
 
     auto hand_back = [&](int i, int why) {     // redo target i on the generic (exact) path
         if (lane == 0) {
@@ -212,6 +251,8 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     if (v & (1 << b)) s_run[off++] = (v >> 4) * 32 + 8 * b;
                 base += __shfl_sync(FULL_MASK, incl, 31);
             }
+            // pad to a whole word of four runs (the expansion reads them four at a time)
+            if (lane < 4 && base + lane < 4 * ng) s_run[base + lane] = 0;
         }
         __syncthreads();
 
@@ -240,17 +281,10 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
             const int i = tile * 32 + tsel;
             if (i >= n) continue;
 
-            float4 pi = a.pw[i];
-            pi.w = fabsf(pi.w);                    // the sign bit is the displaced-node flag
-            const float hA = a.hsml_in[i];
-            const float hB = (float)((double)hA * 1.23);                        // sph.c:51
-            const float hi_w = __fmul_rn(pi.w, norm);                           // wvt_relax.c:124
-            const float hsw = (float)((double)hi_w * a.bx.box_d);               // wvt_relax.c:135
-            const float hA2 = __fmul_rn(hA, hA), hB2 = __fmul_rn(hB, hB), hsw2 = __fmul_rn(hsw, hsw);
-            // wvt_relax.c:167: step * hsml_i * W, W = kW t^8 (...)
-            const float Af = (float)(a.step * (double)hi_w * TF_KW);
-
-            // (1) expand the bit row into a compact candidate-slot list (as in tile.cuh)
+            // (1) expand the bit row into a compact list of particle indices.  Every lane owns
+            //     the words lane, lane+32, ... of the row and writes their hits to one contiguous
+            //     stretch (order inside the list is irrelevant: all sums below are trees); uniform,
+            //     fully unrolled bit loop with predicated stores (tile.cuh).
             constexpr int NW = TL_WORDS / 32;
             unsigned wd[NW];
             int c = 0;
@@ -269,29 +303,49 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
             const int nU = __shfl_sync(FULL_MASK, incl, 31);
             if (nU > TL_UCAP) { hand_back(i, 1); continue; }
             {
-                unsigned short *out = ul + (incl - c);
+                int *out = ul + (incl - c);
 #pragma unroll
                 for (int j = 0; j < NW; j++) {
                     if (j * 32 >= ng) break;               // warp-uniform
                     const unsigned word = wd[j];
-                    const int sbase = (j * 32 + lane) * 32;
+                    const int4 rs = *(const int4 *)(s_run + 4 * (j * 32 + lane));   // the word's four runs
 #pragma unroll
-                    for (int b = 0; b < 32; b++)
-                        if (word & (1u << b)) *out++ = (unsigned short)(sbase + b);
+                    for (int b = 0; b < 32; b++) {
+                        const int first = b < 8 ? rs.x : (b < 16 ? rs.y : (b < 24 ? rs.z : rs.w));
+                        if (word & (1u << b)) *out++ = first + (b & 7);
+                    }
                 }
+                // pad the last batch with the target itself, marked dead by the loop below
+                if (nU + lane < ((nU + 31) & ~31)) ul[nU + lane] = i;
             }
             __syncwarp();
 
+            float4 pi = a.pw[i];
+            pi.w = fabsf(pi.w);                    // the sign bit is the displaced-node flag
+            float hA2, hB2, hsw2, Afy, cn;
+            {
+                const float hA = a.hsml_in[i];
+                const float hB = (float)((double)hA * 1.23);                      // sph.c:51
+                const float hi_w = __fmul_rn(pi.w, norm);                         // wvt_relax.c:124
+                const float hsw = (float)((double)hi_w * a.bx.box_d);             // wvt_relax.c:135
+                hA2 = __fmul_rn(hA, hA); hB2 = __fmul_rn(hB, hB); hsw2 = __fmul_rn(hsw, hsw);
+                // wvt_relax.c:167: step * hsml_i * W, W = kW t^8 (...)
+                Afy = (float)(a.step * (double)hi_w * TF_KW);
+                cn = 0.5f * norm * box;            // pair h in length units: (w_i + w_j) * cn
+                // keep these in registers: recomputing them per batch (what ptxas does under
+                // register pressure) puts conversions and FP64 on the XU pipe inside the hot loop
+                asm volatile("" : "+f"(hA2), "+f"(hB2), "+f"(hsw2), "+f"(Afy), "+f"(cn));
+            }
+
             // (2) classify every hit exactly; separation list (A from the front, "1.23*Hsml
-            //     only" from the back); displacement summed in place
-            int cntA = 0, cntBo = 0, cntW = 0;     // cntW: per-lane until reduced below
+            //     only" from the back); displacement summed in place.  Hits underneath a displaced
+            //     reference node (defect.cuh; ~1e-4 of the particles) are skipped by the hot loop
+            //     and taken by a second pass with the open tests, so that the hot loop has no call.
+            int cntA = 0, baseB = TL_CAP - 1, cntW = 0, npair = 0;   // cntW, npair: per-lane until reduced
             float sx = 0, sy = 0, sz = 0;
-            for (int base = 0; base < nU; base += 32) {
-                const int k = base + lane;
-                const bool live = k < nU;
-                const int slot = live ? ul[k] : 0;
-                const int gidx = s_run[slot >> 3] + (slot & 7);
-                const float4 pj = a.pw[gidx];
+            bool sawflag = false;
+            auto batch = [&](const int k, const int gidx, const float4 pj, auto slow_tag) {
+                constexpr bool SLOW = decltype(slow_tag)::value;
                 const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
                 float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
                 if (!interior) {       // interior tile: no hit can be a periodic image
@@ -299,54 +353,78 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     if (ay > boxhalf) ay = __fsub_rn(ay, box);
                     if (az > boxhalf) az = __fsub_rn(az, box);
                 }
-                const float r2 = sq3_nofma(ax, ay, az);                          // tree.c:88
-                bool inA = live && r2 < hA2, inB = live && r2 < hB2, inW = live && r2 < hsw2;
-                if ((inB | inW) && df_flagged(pj.w)) {
+                float r2 = sq3_nofma(ax, ay, az);                                // tree.c:88
+                const bool flagged = df_flagged(pj.w);
+                // dead lanes: the pad of the last batch, and the hits the other pass takes
+                r2 = (k < nU && flagged == SLOW) ? r2 : 3.0e38f;
+                bool inA = r2 < hA2, inB = r2 < hB2, inW = r2 < hsw2;
+                if (!SLOW) sawflag |= flagged;
+                if (SLOW && (inB | inW)) {
                     const float4 *path = a.dnodes + a.dmap[gidx];
+                    const float hA = a.hsml_in[i];
+                    const float hB = (float)((double)hA * 1.23);
+                    const float hsw = (float)((double)__fmul_rn(pi.w, norm) * a.bx.box_d);
                     if (inA) inA = defect_open(path, pi.x, pi.y, pi.z, hA, box, boxhalf);
                     if (inB) inB = inA || defect_open(path, pi.x, pi.y, pi.z, hB, box, boxhalf);
                     if (inW) inW = defect_open(path, pi.x, pi.y, pi.z, hsw, box, boxhalf);
                 }
-                // r = sqrt(r2): MUFU.RSQ and one Newton step (r2 = 0 is the target itself)
-                const float y = rsqrtf(r2);
+                // r = sqrt(r2): MUFU.RSQ and one Newton step; the target itself (r2 = 0) gives 0
+                const float y = rsqrt_approx(fmaxf(r2, 1e-35f));
                 float r = r2 * y;
                 r = fmaf(0.5f * y, fmaf(-r, r, r2), r);
-                r = r2 > 0.f ? r : 0.f;
                 if (MODE & MODE_DENSITY) {
                     const unsigned mA = __ballot_sync(FULL_MASK, inA);
                     const unsigned mBo = __ballot_sync(FULL_MASK, inB) & ~mA;
-                    if (inA) rl[cntA + __popc(mA & lt)] = r;
-                    else if (inB) rl[TL_CAP - 1 - (cntBo + __popc(mBo & lt))] = r;
+                    const int rank = __popc((inA ? mA : mBo) & lt);
+                    if (inB) rl[inA ? cntA + rank : baseB - rank] = r;
                     cntA += __popc(mA);
-                    cntBo += __popc(mBo);
+                    baseB -= __popc(mBo);
                 }
                 cntW += inW;
                 if (MODE & MODE_WVT) {
                     // wvt_relax.c:137-170; nU <= TL_CAP < NGBMAX: the list cut cannot bite
                     const float hp = (pi.w + fabsf(pj.w)) * cn;                   // :158, length units
-                    const float u = fminf(__fdividef(r, hp), 1.f);                // :160 skip <=> W = 0
+                    const float u = fminf(r * rcp_approx(hp), 1.f);               // :160 skip <=> W = 0
                     const float t = 1.f - u, t2 = t * t, t4 = t2 * t2;
                     const float P = fmaf(fmaf(fmaf(32.f, u, 25.f), u, 8.f), u, 1.f);
-                    const bool use = inW && gidx != i && r2 > 0.f;               // :141
-                    const float f = use ? Af * (t4 * t4) * P * y : 0.f;
+                    const bool use = inW && gidx != i;                           // :141
+                    const float f = use ? (t4 * t4) * P * (Afy * y) : 0.f;
                     // signed closest-image separation: sign(d) * (|d| [- Boxsize])
-                    sx = fmaf(f, copysignf(1.f, dx) * ax, sx);
-                    sy = fmaf(f, copysignf(1.f, dy) * ay, sy);
-                    sz = fmaf(f, copysignf(1.f, dz) * az, sz);
-                    c_pairs += use && u < 1.f;
+                    sx = fmaf(f, __int_as_float(__float_as_int(ax) ^ (__float_as_int(dx) & 0x80000000)), sx);
+                    sy = fmaf(f, __int_as_float(__float_as_int(ay) ^ (__float_as_int(dy) & 0x80000000)), sy);
+                    sz = fmaf(f, __int_as_float(__float_as_int(az) ^ (__float_as_int(dz) & 0x80000000)), sz);
+                    if (use && u < 1.f) npair++;
+                }
+            };
+            {   // the gather of the next batch is in flight while this one is evaluated
+                int g0 = ul[lane];                       // (nU >= 1: the target itself is a hit)
+                float4 p0 = a.pw[g0];
+                for (int k = lane; k < nU + lane; k += 32) {
+                    const int kn = k + 32 < nU + lane ? k + 32 : k;  // (the last batch re-reads itself)
+                    const int g1 = ul[kn];
+                    const float4 p1 = a.pw[g1];
+                    batch(k, g0, p0, std::false_type{});
+                    g0 = g1; p0 = p1;
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cntW += __shfl_xor_sync(FULL_MASK, cntW, o);
+            if (__any_sync(FULL_MASK, sawflag))
+                for (int k = lane; k < nU + lane; k += 32) {
+                    const int g = ul[k];
+                    batch(k, g, a.pw[g], std::true_type{});
+                }
+            const int cntBo = TL_CAP - 1 - baseB;
+            cntW = __reduce_add_sync(FULL_MASK, cntW);
             __syncwarp();
 
-            float h = hA, rho = 0, drho = 0;
+            float h = 0, rho = 0, drho = 0;
             int cnt = 0;
+            unsigned n_search = (MODE & MODE_WVT) ? 1 : 0, n_evals = 0, n_iters = 0;
             if (MODE & MODE_DENSITY) {
                 // (3) the outer loop of sph.c:36-64, as far as the two prepared radii carry it
+                const float hA = a.hsml_in[i];
                 bool ok = true;
                 if (cntA >= TG_DESNNGB) {                    // first search succeeds: Hsml list
-                    cnt = cntA; h = hA; c_search += 1;
+                    cnt = cntA; h = hA; n_search += 1;
                 } else if (cntA + cntBo >= TG_DESNNGB) {     // second search, 1.23*Hsml
                     // bring the entries beyond Hsml next to the others (ascending: a write never
                     // lands on an entry that is still to be read)
@@ -358,43 +436,48 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                         if (q < cntBo) rl[cntA + q] = v;
                         __syncwarp();
                     }
-                    cnt = cntA + cntBo; h = hB; c_search += 2;
+                    cnt = cntA + cntBo; h = (float)((double)hA * 1.23); n_search += 2;
                 } else ok = false;                           // a third search: generic path
                 int why = 3;
                 if (ok) {
+                    // pad to whole passes of 64 (TL_CAP is a multiple of 64)
+                    const int cnt64 = (cnt + 63) & ~63;
+                    if (cnt + lane < cnt64) rl[cnt + lane] = 3.0e38f;
+                    if (cnt + 32 + lane < cnt64) rl[cnt + 32 + lane] = 3.0e38f;
                     __syncwarp();
-                    ok = find_hsml_fast(a, rl, cnt, h, rho, drho, c_evals, c_iters);
+                    ok = find_hsml_fast(a, rl, cnt, h, rho, drho, n_evals, n_iters);
                     why = 4;                                 // no convergence on the frozen list
                 }
                 if (!ok) { hand_back(i, why); continue; }
             }
-            c_search += (MODE & MODE_WVT) ? 1 : 0;
-            c_gath += max(cnt, cntW);
 
             // (4) results
             double dsx = 0, dsy = 0, dsz = 0;
-            if (MODE & MODE_WVT) { dsx = warp_sum((double)sx); dsy = warp_sum((double)sy); dsz = warp_sum((double)sz); }
+            if (MODE & MODE_WVT) {
+                dsx = warp_sum((double)sx); dsy = warp_sum((double)sy); dsz = warp_sum((double)sz);
+                npair = __reduce_add_sync(FULL_MASK, npair);
+            }
             if (lane == 0) {
                 if (MODE & MODE_DENSITY) {                                       // sph.c:66-70
                     const float q = __fmul_rn(__fdiv_rn(h, __fmul_rn(3.f, rho)), drho);
                     a.hsml_out[i] = h;
                     a.rho_out[i] = rho;
-                    a.varh_out[i] = (float)(1.0 / (double)__fadd_rn(1.f, q));
+                    a.varh_out[i] = __frcp_rn(__fadd_rn(1.f, q));
                 }
                 if (MODE & MODE_WVT) {
                     a.delta[i] = (float)dsx;
                     a.delta[n + i] = (float)dsy;
                     a.delta[2 * (size_t)n + i] = (float)dsz;
                 }
+                cw[0] += n_evals + npair; cw[1] += max(cnt, cntW); cw[2] += n_search; cw[3] += n_iters;
             }
         }
     }
 
-    const unsigned long long pairs = warp_sum_u64(c_pairs);
     if (lane == 0) {
-        atomicAdd(&a.counters[0], c_evals + pairs);
-        atomicAdd(&a.counters[1], c_gath);
-        atomicAdd(&a.counters[2], (unsigned long long)c_search);
-        atomicAdd(&a.counters[3], (unsigned long long)c_iters);
+        atomicAdd(&a.counters[0], cw[0]);
+        atomicAdd(&a.counters[1], cw[1]);
+        atomicAdd(&a.counters[2], cw[2]);
+        atomicAdd(&a.counters[3], cw[3]);
     }
 }

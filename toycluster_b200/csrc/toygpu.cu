@@ -33,6 +33,8 @@
 #include "tile.cuh"
 #include "tile_fast.cuh"
 #include "bfield.cuh"
+#include "comm.cuh"
+#include <thread>
 
 static thread_local std::string g_create_error;
 
@@ -102,6 +104,21 @@ struct tg_ctx {
     int tile_blocks = 0, fast_blocks = 0;
     bool use_tiles = true;
 
+    // AoS records of the driver, resident on the device (tg_upload / tg_download)
+    unsigned char *rawP = nullptr, *rawS = nullptr, *outP = nullptr, *outS = nullptr;
+    size_t raw_pstride = 0, raw_sstride = 0;
+    bool have_raw = false;
+    std::vector<void *> pinned;     // host ranges registered by tg_pin_host
+
+    // multi-GPU (comm.cuh): one communicator per rank context; a GROUP context (tg_config.ngpus
+    // > 1) owns one rank context per device and runs every operator on all of them
+    HaloExtra *halo_extra = nullptr;   // tg_make_magnetic_field scratch
+    int *n_limited = nullptr;
+    int *ngb_scratch = nullptr;        // tg_find_ngb
+    ncclComm_t comm = nullptr;
+    double *errbuf = nullptr;       // [3 * nranks] gathered (err sum, err max, stop flag)
+    std::vector<tg_ctx *> kids;
+
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     tg_stats stats{};
     unsigned long long launches = 0;
@@ -117,6 +134,33 @@ static int fail(tg_ctx *c, int code, const char *fmt, ...)
     if (c) c->err = buf; else g_create_error = buf;
     return code;
 }
+
+ // Run `fn` on every rank context of a group, one host thread per device (the operators block on
+// their own stream; NCCL calls of different ranks must be in flight together).
+template <class F> static int group_run(tg_ctx *g, F fn)
+{
+    const size_t m = g->kids.size();
+    std::vector<int> rc(m, 0);
+    std::vector<std::thread> th;
+    for (size_t r = 1; r < m; r++) th.emplace_back([&, r] { rc[r] = fn(g->kids[r]); });
+    rc[0] = fn(g->kids[0]);
+    for (auto &t : th) t.join();
+    for (size_t r = 0; r < m; r++)
+        if (rc[r]) { g->err = "rank " + std::to_string(r) + ": " + g->kids[r]->err; return rc[r]; }
+    return TG_OK;
+}
+#define TG_GROUP(c, call)                                                             \
+    if ((c) && !(c)->kids.empty()) return group_run((c), [&](tg_ctx *k) { return call; })
+#define TG_NOGROUP(c, name)                                                           \
+    if ((c) && !(c)->kids.empty())                                                    \
+        return fail((c), TG_EINVAL, name ": not available on a multi-GPU group context")
+#define TG_GROUP0(c, call)                                                            \
+    if ((c) && !(c)->kids.empty()) {                                                  \
+        tg_ctx *k = (c)->kids[0];                                                     \
+        const int rc_ = call;                                                         \
+        if (rc_) (c)->err = k->err;                                                   \
+        return rc_;                                                                   \
+    }
 
 #define CU(call)                                                                      \
     do {                                                                              \
@@ -142,6 +186,36 @@ template <class T> static cudaError_t dmalloc(T **p, size_t count)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ------------------------------------------------------------------ collectives (comm.cuh)
+
+#define NC(call)                                                                      \
+    do {                                                                              \
+        ncclResult_t r_ = (call);                                                     \
+        if (r_ != ncclSuccess)                                                        \
+            return fail(c, TG_ECUDA, "%s failed: %s (%s:%d)", #call,                  \
+                        nccl_api()->GetErrorString(r_), __FILE__, __LINE__);          \
+    } while (0)
+
+// In-place all-gather of an array of nranks*chunk records of `rec_bytes` bytes, this rank's
+// records already in place.  No-op without a communicator.
+static int gather_slices(tg_ctx *c, void *base, size_t rec_bytes)
+{
+    if (!c->comm) return TG_OK;
+    const size_t per_rank = (size_t)c->chunk * rec_bytes;
+    NC(nccl_api()->AllGather((const char *)base + (size_t)c->cfg.rank * per_rank, base, per_rank, ncclInt8,
+                             c->comm, c->stream));
+    return TG_OK;
+}
+
+// max over ranks of `count` ints on the device (status / cold flags): every rank must take the
+// same branch afterwards, or the next collective would hang.
+static int reduce_flags_max(tg_ctx *c, int *dev, int count)
+{
+    if (!c->comm) return TG_OK;
+    NC(nccl_api()->AllReduce(dev, dev, count, ncclInt32, ncclMax, c->comm, c->stream));
+    return TG_OK;
+}
+
 // ------------------------------------------------------------------ life cycle
 
 extern "C" const char *tg_last_error(const tg_ctx *c)
@@ -152,7 +226,17 @@ extern "C" const char *tg_last_error(const tg_ctx *c)
 extern "C" int tg_destroy(tg_ctx *c)
 {
     if (!c) return TG_OK;
+    if (!c->kids.empty()) {
+        for (tg_ctx *k : c->kids) tg_destroy(k);
+        delete c;
+        return TG_OK;
+    }
     cudaSetDevice(c->cfg.device);
+    if (c->comm) nccl_api()->CommDestroy(c->comm);
+    if (c->errbuf) cudaFree(c->errbuf);
+    if (c->halo_extra) cudaFree(c->halo_extra);
+    if (c->n_limited) cudaFree(c->n_limited);
+    if (c->ngb_scratch) cudaFree(c->ngb_scratch);
     void *ptrs[] = {c->posh, c->id, c->apot, c->stage, c->key_hi, c->key_lo, c->key_tmp, c->idx, c->idx_tmp,
                     c->hist, c->pw, c->soa, c->hsml_in, c->rho_model, c->rm_state, c->rm_state_s, c->id_s, c->key_lo_s, c->apot_s,
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->sub_mem, c->cpl,
@@ -160,6 +244,8 @@ extern "C" int tg_destroy(tg_ctx *c)
                     c->flags, c->counters, c->gscratch, c->tile_ng, c->tile_groups, c->worklist,
                     c->defect.events, c->defect.big, c->defect.counts, c->defect.nodes, c->defect.dmap};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : {(void *)c->rawP, (void *)c->rawS, (void *)c->outP, (void *)c->outS}) if (p) cudaFree(p);
+    for (void *h : c->pinned) cudaHostUnregister(h);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -175,6 +261,46 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
         return fail(c, TG_EINVAL, "tg_create: n_gas, boxsize and mpart_gas must be positive");
     if ((cfg->flags & TG_FAST) && (cfg->flags & TG_WVT_SEQUENTIAL))
         return fail(c, TG_EINVAL, "tg_create: TG_FAST and TG_WVT_SEQUENTIAL exclude each other");
+    if (cfg->ngpus > 1) {
+        // group context: one rank context per device + one communicator each (ncclCommInitAll)
+        NcclApi *api = nccl_api();
+        if (!api->ok) return fail(c, TG_EINVAL, "tg_create: ngpus = %d needs NCCL: %s", cfg->ngpus, api->why);
+        if (cfg->nranks > 1) return fail(c, TG_EINVAL, "tg_create: ngpus and rank/nranks exclude each other");
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < cfg->ngpus)
+            return fail(c, TG_EINVAL, "tg_create: ngpus = %d but %d CUDA device(s) visible", cfg->ngpus, ndev);
+        tg_ctx *g = new tg_ctx;
+        g->cfg = *cfg;
+        g->n = cfg->n_gas;
+        std::vector<int> devs(cfg->ngpus);
+        for (int r = 0; r < cfg->ngpus; r++) devs[r] = cfg->devices ? cfg->devices[r] : r;
+        for (int r = 0; r < cfg->ngpus; r++) {
+            tg_config kc = *cfg;
+            kc.ngpus = 0; kc.devices = nullptr; kc.stream = nullptr;
+            kc.device = devs[r]; kc.rank = r; kc.nranks = cfg->ngpus;
+            tg_ctx *k = nullptr;
+            const int rc = tg_create(&k, &kc);
+            if (rc) { tg_destroy(g); return rc; }
+            g->kids.push_back(k);
+        }
+        std::vector<ncclComm_t> comms(cfg->ngpus);
+        ncclResult_t nr = api->CommInitAll(comms.data(), cfg->ngpus, devs.data());
+        if (nr != ncclSuccess) {
+            tg_destroy(g);
+            return fail(nullptr, TG_ECUDA, "ncclCommInitAll failed: %s", api->GetErrorString(nr));
+        }
+        for (int r = 0; r < cfg->ngpus; r++) {
+            tg_ctx *k = g->kids[r];
+            k->comm = comms[r];
+            cudaSetDevice(k->cfg.device);
+            if (cudaMalloc((void **)&k->errbuf, sizeof(double) * 3 * cfg->ngpus) != cudaSuccess) {
+                tg_destroy(g);
+                return fail(nullptr, TG_ENOMEM, "tg_create: device memory");
+            }
+        }
+        *out = g;
+        return TG_OK;
+    }
     const int nranks = cfg->nranks > 0 ? cfg->nranks : 1;
     if (cfg->rank < 0 || cfg->rank >= nranks)
         return fail(c, TG_EINVAL, "tg_create: rank %d outside [0,%d)", cfg->rank, nranks);
@@ -245,12 +371,12 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     CUC(dmalloc(&c->rho, npad));
     CUC(dmalloc(&c->varh, npad));
     CUC(dmalloc(&c->delta, (size_t)3 * n));
-    CUC(dmalloc(&c->bfld, (size_t)3 * n));
+    CUC(dmalloc(&c->bfld, (size_t)3 * npad));
     CUC(cudaMemsetAsync(c->rho, 0, sizeof(float) * n, c->stream));
     CUC(cudaMemsetAsync(c->varh, 0, sizeof(float) * n, c->stream));
     CUC(cudaMemsetAsync(c->rho_model, 0, sizeof(float) * n, c->stream));
     CUC(cudaMemsetAsync(c->delta, 0, sizeof(float) * 3 * n, c->stream));
-    CUC(cudaMemsetAsync(c->bfld, 0, sizeof(float) * 3 * n, c->stream));
+    CUC(cudaMemsetAsync(c->bfld, 0, sizeof(float) * 3 * npad, c->stream));
 
     // index levels
     Bvh &t = c->bvh;
@@ -362,8 +488,38 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     return TG_OK;
 }
 
+// One process per GPU: rank 0 calls tg_comm_id, ships the 128 bytes to the other ranks by
+// whatever channel the host has (MPI, torch.distributed, a file), every rank calls tg_comm_init.
+extern "C" int tg_comm_id(unsigned char *id128)
+{
+    tg_ctx *c = nullptr;
+    NcclApi *api = nccl_api();
+    if (!id128) return fail(c, TG_EINVAL, "tg_comm_id: null argument");
+    if (!api->ok) return fail(c, TG_EINVAL, "tg_comm_id: NCCL unavailable: %s", api->why);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    NC(api->GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return TG_OK;
+}
+
+extern "C" int tg_comm_init(tg_ctx *c, const unsigned char *id128)
+{
+    if (!c || !id128) return fail(c, TG_EINVAL, "tg_comm_init: null argument");
+    if (!c->kids.empty() || c->comm) return fail(c, TG_EINVAL, "tg_comm_init: context already has a communicator");
+    NcclApi *api = nccl_api();
+    if (!api->ok) return fail(c, TG_EINVAL, "tg_comm_init: NCCL unavailable: %s", api->why);
+    CU(cudaSetDevice(c->cfg.device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NC(api->CommInitRank(&c->comm, c->cfg.nranks, id, c->cfg.rank));
+    CU(dmalloc(&c->errbuf, (size_t)3 * c->cfg.nranks));
+    return TG_OK;
+}
+
 extern "C" int tg_set_halos(tg_ctx *c, int n, const tg_halo *h)
 {
+    TG_GROUP(c, tg_set_halos(k, n, h));
     if (!c || n < 0 || n > MAX_HALOS || (n && !h)) return fail(c, TG_EINVAL, "tg_set_halos: bad arguments (max %d rows)", MAX_HALOS);
     CU(cudaSetDevice(c->cfg.device));
     std::vector<Halo> rows(n);
@@ -400,6 +556,7 @@ static int upload_common(tg_ctx *c, const float *pos, const float *hsml)
     c->any_cold = cold != 0;
     c->index_valid = false;
     c->have_apot = false;
+    c->have_raw = false;
     CU(cudaMemsetAsync(c->rm_state, 0, sizeof(float) * n, c->stream));
     return TG_OK;
 }
@@ -407,6 +564,18 @@ static int upload_common(tg_ctx *c, const float *pos, const float *hsml)
 extern "C" int tg_upload_soa(tg_ctx *c, const float *pos, const float *hsml)
 {
     if (!c || !pos) return fail(c, TG_EINVAL, "tg_upload_soa: null argument");
+    TG_GROUP(c, tg_upload_soa(k, pos, hsml));
+    if (c->comm) {       // every rank ships its own slice over PCIe; NVLink does the rest
+        int rc = tg_upload_soa_slice(c, pos, hsml, nullptr);
+        if (rc) return rc;
+        if ((rc = gather_slices(c, c->posh, sizeof(float4)))) return rc;
+        if ((rc = reduce_flags_max(c, c->flags + 4, 1))) return rc;
+        int cold = 0;
+        CU(cudaMemcpyAsync(&cold, c->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->any_cold = cold != 0;
+        return TG_OK;
+    }
     return upload_common(c, pos, hsml);
 }
 
@@ -416,6 +585,7 @@ extern "C" int tg_upload_soa(tg_ctx *c, const float *pos, const float *hsml)
 extern "C" int tg_upload_soa_slice(tg_ctx *c, const float *pos, const float *hsml, int *cold_out)
 {
     if (!c || !pos) return fail(c, TG_EINVAL, "tg_upload_soa_slice: null argument");
+    TG_NOGROUP(c, "tg_upload_soa_slice");
     const int n = c->n, lo = c->lo, m = c->hi - c->lo;
     CU(cudaSetDevice(c->cfg.device));
     CU(cudaMemsetAsync(c->flags + 4, 0, sizeof(int), c->stream));
@@ -435,6 +605,7 @@ extern "C" int tg_upload_soa_slice(tg_ctx *c, const float *pos, const float *hsm
     c->any_cold = cold != 0;
     c->index_valid = false;
     c->have_apot = false;
+    c->have_raw = false;
     CU(cudaMemsetAsync(c->rm_state, 0, sizeof(float) * n, c->stream));
     if (cold_out) *cold_out = cold;
     return TG_OK;
@@ -443,6 +614,7 @@ extern "C" int tg_upload_soa_slice(tg_ctx *c, const float *pos, const float *hsm
 extern "C" int tg_set_cold(tg_ctx *c, int any_cold)
 {
     if (!c) return TG_EINVAL;
+    TG_GROUP(c, tg_set_cold(k, any_cold));
     c->any_cold = any_cold != 0;
     return TG_OK;
 }
@@ -451,6 +623,7 @@ extern "C" int tg_set_cold(tg_ctx *c, int any_cold)
 extern "C" int tg_download_soa_slice(tg_ctx *c, float *pos, float *hsml)
 {
     if (!c) return TG_EINVAL;
+    TG_GROUP(c, tg_download_soa_slice(k, pos, hsml));
     CU(cudaSetDevice(c->cfg.device));
     const int n = c->n, lo = c->lo, m = c->hi - c->lo;
     if (m > 0 && (pos || hsml)) {
@@ -463,29 +636,135 @@ extern "C" int tg_download_soa_slice(tg_ctx *c, float *pos, float *hsml)
     return TG_OK;
 }
 
+// ---- the driver's AoS records (globals.h:161-180) ---------------------------------------
+// The raw records cross the bus once per call (124 B per particle: 1.24 GB at 10 M) and are
+// unpacked, permuted and patched ON THE DEVICE; the host does no per-particle work.
+
+__global__ void k_unpack_records(int n, const unsigned char *__restrict__ rawP, size_t pstride,
+                                 const unsigned char *__restrict__ rawS, size_t sstride,
+                                 float4 *__restrict__ posh, int *__restrict__ id, float *__restrict__ apot,
+                                 float *__restrict__ rm, int *__restrict__ cold_flag)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float *pp = (const float *)(rawP + (size_t)k * pstride);       // Pos @ +0
+    const float *sp = (const float *)(rawS + (size_t)k * sstride);
+    const float h = sp[2];                                               // Hsml @ +8
+    posh[k] = make_float4(pp[0], pp[1], pp[2], h);
+    id[k] = k;
+    if (apot) { apot[3 * (size_t)k] = sp[7]; apot[3 * (size_t)k + 1] = sp[8]; apot[3 * (size_t)k + 2] = sp[9]; }   // Apot @ +28
+    rm[k] = sstride >= 48 ? sp[11] : 0.f;                                // Rho_Model @ +44
+    if (h == 0.f) *cold_flag = 1;
+}
+
+// out record k = in record id[k], in 4-byte words (peano.c:96-117 moves whole structs).
+__global__ void k_gather_records(size_t total_words, int wpr, const int *__restrict__ id,
+                                 const uint32_t *__restrict__ in, uint32_t *__restrict__ out)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_words) return;
+    const size_t rec = t / wpr;
+    const int w = (int)(t - rec * wpr);
+    out[t] = in[(size_t)id[rec] * wpr + w];
+}
+
+// The fields the path owns, written over the permuted records.
+__global__ void k_patch_records(int n, int first, unsigned char *__restrict__ outP, size_t pstride,
+                                unsigned char *__restrict__ outS, size_t sstride,
+                                const float4 *__restrict__ posh, const uint64_t *__restrict__ key_lo,
+                                const uint64_t *__restrict__ key_hi, const float *__restrict__ rho,
+                                const float *__restrict__ varh, const float *__restrict__ bfld,
+                                const float *__restrict__ rm)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t *p = (uint32_t *)(outP + (size_t)k * pstride);
+    float *g = (float *)(outS + (size_t)k * sstride);
+    const float4 ph = posh[k];
+    ((float *)p)[0] = ph.x; ((float *)p)[1] = ph.y; ((float *)p)[2] = ph.z;    // Pos @ +0
+    if (key_lo) {
+        const uint64_t lo = key_lo[k], hi = key_hi[k];
+        p[8] = (uint32_t)lo; p[9] = (uint32_t)(lo >> 32);                  // Key @ +32 (little endian u128)
+        p[10] = (uint32_t)hi; p[11] = (uint32_t)(hi >> 32);
+        p[12] = (uint32_t)((first + k) / 32);                              // Tree_Parent @ +48: index group
+    }                                                                      // (tree.c's node ids are private)
+    g[1] = rho[k];                                                         // Rho @ +4
+    g[2] = ph.w;                                                           // Hsml @ +8
+    g[3] = varh[k];                                                        // VarHsmlFac @ +12
+    g[4] = bfld[3 * (size_t)k]; g[5] = bfld[3 * (size_t)k + 1]; g[6] = bfld[3 * (size_t)k + 2];   // Bfld @ +16
+    g[11] = rm[k];                                                         // Rho_Model @ +44
+}
+
+extern "C" int tg_pin_host(tg_ctx *c, void *ptr, size_t bytes)
+{
+    if (!c || !ptr || !bytes) return fail(c, TG_EINVAL, "tg_pin_host: bad arguments");
+    TG_GROUP0(c, tg_pin_host(k, ptr, bytes));     // portable registration: valid on every device
+    CU(cudaSetDevice(c->cfg.device));
+    for (void *h : c->pinned) if (h == ptr) return TG_OK;
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    c->pinned.push_back(ptr);
+    return TG_OK;
+}
+
+extern "C" int tg_unpin_host(tg_ctx *c, void *ptr)
+{
+    if (!c || !ptr) return TG_EINVAL;
+    TG_GROUP0(c, tg_unpin_host(k, ptr));
+    for (size_t k = 0; k < c->pinned.size(); k++)
+        if (c->pinned[k] == ptr) {
+            cudaHostUnregister(ptr);
+            c->pinned.erase(c->pinned.begin() + k);
+            return TG_OK;
+        }
+    return fail(c, TG_EINVAL, "tg_unpin_host: range was not pinned by tg_pin_host");
+}
+
 extern "C" int tg_upload(tg_ctx *c, const void *P, size_t p_stride, const void *SphP, size_t s_stride)
 {
-    if (!c || !P || !SphP || p_stride < 12 || s_stride < 12)
-        return fail(c, TG_EINVAL, "tg_upload: bad arguments");
-    std::vector<float> pos((size_t)3 * c->n), hsml(c->n), rhom(c->n, 0.f);
-    std::vector<float> apot((size_t)3 * c->n);
-    const bool with_apot = s_stride >= 40, with_rhom = s_stride >= 48;
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < c->n; i++) {
-        const float *pp = (const float *)((const char *)P + i * p_stride);             // Pos @ +0
-        const float *sph = (const float *)((const char *)SphP + i * s_stride);
-        pos[3 * (size_t)i] = pp[0]; pos[3 * (size_t)i + 1] = pp[1]; pos[3 * (size_t)i + 2] = pp[2];
-        hsml[i] = sph[2];                                                               // Hsml @ +8
-        if (with_apot) for (int k = 0; k < 3; k++) apot[3 * (size_t)i + k] = sph[7 + k];   // Apot @ +28
-        if (with_rhom) rhom[i] = sph[11];                                               // Rho_Model @ +44
+    if (!c || !P || !SphP || p_stride < 12 || s_stride < 12 || p_stride % 4 || s_stride % 4)
+        return fail(c, TG_EINVAL, "tg_upload: bad arguments (strides must be multiples of 4 and hold Pos / Hsml)");
+    TG_GROUP(c, tg_upload(k, P, p_stride, SphP, s_stride));
+    if (c->cfg.nranks > 1 && !c->comm)
+        return fail(c, TG_EINVAL, "tg_upload with nranks > 1 needs a communicator (tg_comm_init or tg_config.ngpus)");
+    const int n = c->n;
+    CU(cudaSetDevice(c->cfg.device));
+    if (!c->rawP || c->raw_pstride != p_stride || c->raw_sstride != s_stride) {
+        for (unsigned char **p : {&c->rawP, &c->rawS, &c->outP, &c->outS}) { if (*p) cudaFree(*p); *p = nullptr; }
+        const size_t npad = (size_t)c->chunk * c->cfg.nranks;      // room for the in-place all-gather
+        CU(dmalloc(&c->rawP, npad * p_stride));
+        CU(dmalloc(&c->rawS, npad * s_stride));
+        CU(dmalloc(&c->outP, npad * p_stride));
+        CU(dmalloc(&c->outS, npad * s_stride));
+        c->raw_pstride = p_stride;
+        c->raw_sstride = s_stride;
     }
-    int rc = upload_common(c, pos.data(), hsml.data());
-    if (rc == TG_OK && with_apot) rc = tg_set_apot(c, apot.data());
-    if (rc == TG_OK && with_rhom) {
-        CU(cudaMemcpyAsync(c->rm_state, rhom.data(), sizeof(float) * c->n, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+    const bool with_apot = s_stride >= 40;
+    if (with_apot && !c->apot) {
+        CU(dmalloc(&c->apot, (size_t)3 * n));
+        CU(dmalloc(&c->apot_s, (size_t)3 * n));
     }
-    return rc;
+    // DMA when the host ranges are pinned (tg_pin_host), staged by the driver otherwise
+    // (with a communicator: only this rank's slice crosses PCIe, NVLink all-gathers the rest)
+    const size_t lo = c->comm ? c->lo : 0, m = c->comm ? c->hi - c->lo : n;
+    if (m) {
+        CU(cudaMemcpyAsync(c->rawP + lo * p_stride, (const char *)P + lo * p_stride, m * p_stride, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->rawS + lo * s_stride, (const char *)SphP + lo * s_stride, m * s_stride, cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc;
+    if ((rc = gather_slices(c, c->rawP, p_stride))) return rc;
+    if ((rc = gather_slices(c, c->rawS, s_stride))) return rc;
+    CU(cudaMemsetAsync(c->flags + 4, 0, sizeof(int), c->stream));
+    k_unpack_records<<<cdiv(n, 256), 256, 0, c->stream>>>(n, c->rawP, p_stride, c->rawS, s_stride, c->posh, c->id,
+                                                         with_apot ? c->apot : nullptr, c->rm_state, c->flags + 4);
+    LAUNCH_CHECK();
+    int cold = 0;
+    CU(cudaMemcpyAsync(&cold, c->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->any_cold = cold != 0;
+    c->index_valid = false;
+    c->have_apot = with_apot;
+    c->have_raw = true;
+    return TG_OK;
 }
 
 // apot is given in the CURRENT order of the context (upload order right after an upload,
@@ -493,6 +772,7 @@ extern "C" int tg_upload(tg_ctx *c, const void *P, size_t p_stride, const void *
 extern "C" int tg_set_apot(tg_ctx *c, const float *apot)
 {
     if (!c || !apot) return fail(c, TG_EINVAL, "tg_set_apot: null argument");
+    TG_GROUP(c, tg_set_apot(k, apot));
     CU(cudaSetDevice(c->cfg.device));
     if (!c->apot) {
         CU(dmalloc(&c->apot, (size_t)3 * c->n));
@@ -704,6 +984,10 @@ template <int MODE> static int launch_sweep(tg_ctx *c, const SweepArgs &a)
 static int check_flags(tg_ctx *c)
 {
     int f[4], dc[4];
+    {   // a rank that fails must take the others with it, or their next collective hangs
+        const int rc = reduce_flags_max(c, c->flags + 1, 2);
+        if (rc) return rc;
+    }
     CU(cudaMemcpyAsync(f, c->flags, sizeof f, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(dc, c->defect.counts, sizeof dc, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -732,6 +1016,15 @@ static int carry_state(tg_ctx *c)
         k_carry<<<cdiv(c->hi - c->lo, 256), 256, 0, c->stream>>>(c->lo, c->hi, c->pw, c->hsml_out, c->posh);
     LAUNCH_CHECK();
     return TG_OK;
+}
+
+// After a sweep: every rank holds every slice again (collective 2).
+static int gather_state(tg_ctx *c, bool with_density)
+{
+    int rc = gather_slices(c, c->posh, sizeof(float4));
+    if (rc || !with_density) return rc;
+    if ((rc = gather_slices(c, c->rho, sizeof(float)))) return rc;
+    return gather_slices(c, c->varh, sizeof(float));
 }
 
 static int error_pass(tg_ctx *c, double *err_max, double *err_mean)
@@ -798,6 +1091,7 @@ static int finish_stats(tg_ctx *c, bool have_sweep_events)
 extern "C" int tg_find_sph_quantities(tg_ctx *c)
 {
     if (!c) return TG_EINVAL;
+    TG_GROUP(c, tg_find_sph_quantities(k));
     CU(cudaSetDevice(c->cfg.device));
     int rc = reset_counters(c);
     if (rc) return rc;
@@ -807,6 +1101,7 @@ extern "C" int tg_find_sph_quantities(tg_ctx *c)
     if ((rc = density_pass(c))) return rc;
     CU(cudaEventRecord(c->ev[3], c->stream));
     if ((rc = carry_state(c))) return rc;
+    if ((rc = gather_state(c, true))) return rc;
     CU(cudaEventRecord(c->ev[1], c->stream));
     if ((rc = check_flags(c))) return rc;
     return finish_stats(c, true);
@@ -819,6 +1114,19 @@ extern "C" int tg_find_sph_quantities(tg_ctx *c)
 extern "C" int tg_wvt_begin(tg_ctx *c, double step_guess, double *err_sum, double *err_max, int *count)
 {
     if (!c) return TG_EINVAL;
+    if (!c->kids.empty()) {      // every rank returns the same global numbers
+        const int rc = group_run(c, [&](tg_ctx *k) {
+            double s = 0, m = 0; int cnt = 0;
+            const int r = tg_wvt_begin(k, step_guess, &s, &m, &cnt);
+            if (r == TG_OK && k == c->kids[0]) {
+                if (err_sum) *err_sum = s;
+                if (err_max) *err_max = m;
+                if (count) *count = cnt;
+            }
+            return r;
+        });
+        return rc;
+    }
     CU(cudaSetDevice(c->cfg.device));
     int rc = reset_counters(c);
     if (rc) return rc;
@@ -837,9 +1145,21 @@ extern "C" int tg_wvt_begin(tg_ctx *c, double step_guess, double *err_sum, doubl
     double emax = 0, emean = 0;
     if ((rc = error_pass(c, &emax, &emean))) return rc;      // wvt_relax.c:73-87
     if ((rc = check_flags(c))) return rc;
-    if (err_sum) *err_sum = emean * (c->hi - c->lo);
+    double esum = emean * (c->hi - c->lo);
+    int cnt = c->hi - c->lo;
+    if (c->comm) {       // SURVEY 8e, collective 3: the statistics of all ranks, reduced in rank order
+        const int R = c->cfg.nranks;
+        NC(nccl_api()->AllGather(c->scal + 1, c->errbuf, 2, ncclFloat64, c->comm, c->stream));
+        std::vector<double> h(2 * R);
+        CU(cudaMemcpyAsync(h.data(), c->errbuf, sizeof(double) * 2 * R, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        esum = 0; emax = 0;
+        for (int r = 0; r < R; r++) { esum += h[2 * r]; emax = std::max(emax, h[2 * r + 1]); }
+        cnt = c->n;
+    }
+    if (err_sum) *err_sum = esum;
     if (err_max) *err_max = emax;
-    if (count) *count = c->hi - c->lo;
+    if (count) *count = cnt;
     return TG_OK;
 }
 
@@ -849,6 +1169,7 @@ extern "C" int tg_wvt_begin(tg_ctx *c, double step_guess, double *err_sum, doubl
 extern "C" int tg_wvt_finish(tg_ctx *c, double step_final)
 {
     if (!c) return TG_EINVAL;
+    TG_GROUP(c, tg_wvt_finish(k, step_final));
     CU(cudaSetDevice(c->cfg.device));
     int rc;
     if (step_final <= 0) {
@@ -862,6 +1183,7 @@ extern "C" int tg_wvt_finish(tg_ctx *c, double step_final)
         }
         if ((rc = move_pass(c, scale))) return rc;
     }
+    if ((rc = gather_state(c, true))) return rc;
     CU(cudaEventRecord(c->ev[1], c->stream));
     return finish_stats(c, true);
 }
@@ -880,9 +1202,19 @@ extern "C" int tg_wvt_iteration(tg_ctx *c, double step, double *err_max, double 
 extern "C" int tg_regularise(tg_ctx *c, int max_iters, tg_log_fn log, void *user, int *iters_done)
 {
     if (!c) return TG_EINVAL;
-    if (c->cfg.nranks > 1)
+    if (!c->kids.empty()) {      // the loop runs on every rank; rank 0 talks to the observer
+        return group_run(c, [&](tg_ctx *k) {
+            int done = 0;
+            const bool first = k == c->kids[0];
+            const int r = tg_regularise(k, max_iters, first ? log : nullptr, user, &done);
+            if (first && iters_done) *iters_done = done;
+            return r;
+        });
+    }
+    if (c->cfg.nranks > 1 && !c->comm)
         return fail(c, TG_EINVAL, "tg_regularise needs the global error statistics: with nranks > 1 "
-                                  "drive tg_wvt_begin / tg_wvt_finish and all-reduce in between");
+                                  "call tg_comm_init first (or drive tg_wvt_begin / tg_wvt_finish and "
+                                  "all-reduce in between)");
     // wvt_relax.c:46-59
     int it = -1, started = 0;
     double step = 0.0085;
@@ -900,6 +1232,12 @@ extern "C" int tg_regularise(tg_ctx *c, int max_iters, tg_log_fn log, void *user
         const double errMean = errSum / cnt;                 // wvt_relax.c:87
         errDiff = (errLast - errMean) / errMean;             // wvt_relax.c:89
         int stop = log ? log(it, errMax, errMean, errDiff, step, user) : 0;
+        if (c->comm) {           // the observer lives on one rank: everybody must hear its verdict
+            CU(cudaMemcpyAsync(c->flags + 7, &stop, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            if ((rc = reduce_flags_max(c, c->flags + 7, 1))) return rc;
+            CU(cudaMemcpyAsync(&stop, c->flags + 7, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
 
         bool leave = stop != 0;
         if (errDiff < 0.01 && it > 25) leave = true;         // wvt_relax.c:94
@@ -920,6 +1258,7 @@ extern "C" int tg_regularise(tg_ctx *c, int max_iters, tg_log_fn log, void *user
 extern "C" int tg_bfld_from_rotA(tg_ctx *c)
 {
     if (!c) return TG_EINVAL;
+    TG_GROUP(c, tg_bfld_from_rotA(k));
     if (!c->index_valid) return fail(c, TG_EINVAL, "tg_bfld_from_rotA: no index (call tg_find_sph_quantities first, sph.c:229 reuses the tree)");
     if (!c->have_apot) return fail(c, TG_EINVAL, "tg_bfld_from_rotA: Apot not set");
     CU(cudaSetDevice(c->cfg.device));
@@ -931,20 +1270,39 @@ extern "C" int tg_bfld_from_rotA(tg_ctx *c)
     CU(cudaEventRecord(c->ev[2], c->stream));
     if ((rc = launch_sweep<MODE_ROTA>(c, a))) return rc;
     CU(cudaEventRecord(c->ev[3], c->stream));
+    if ((rc = gather_slices(c, c->bfld, 3 * sizeof(float)))) return rc;
     CU(cudaEventRecord(c->ev[1], c->stream));
+    if ((rc = check_flags(c))) return rc;
     return finish_stats(c, true);
 }
 
 extern "C" int tg_make_magnetic_field(tg_ctx *c, const tg_bfield *par, double *norm_out, int *n_limited_out)
 {
     if (!c || !par) return TG_EINVAL;
+    if (!c->kids.empty()) {
+        return group_run(c, [&](tg_ctx *k) {
+            double norm = 0; int lim = 0;
+            const int r = tg_make_magnetic_field(k, par, &norm, &lim);
+            if (r == TG_OK && k == c->kids[0]) {
+                if (norm_out) *norm_out = norm;
+                if (n_limited_out) *n_limited_out = lim;
+            }
+            return r;
+        });
+    }
     if (!c->index_valid) return fail(c, TG_EINVAL, "tg_make_magnetic_field: no index (call tg_find_sph_quantities first)");
     if (c->nhalos == 0) return fail(c, TG_EINVAL, "tg_set_halos has not been called");
+    if (c->cfg.nranks > 1 && !c->comm)
+        return fail(c, TG_EINVAL, "tg_make_magnetic_field with nranks > 1 needs a communicator (the field maximum is global)");
     CU(cudaSetDevice(c->cfg.device));
     const int n = c->n, T = 256;
     if (!c->apot) {
         CU(dmalloc(&c->apot, (size_t)3 * n));
         CU(dmalloc(&c->apot_s, (size_t)3 * n));
+    }
+    if (!c->halo_extra) {                       // persistent scratch: nothing to leak on an early return
+        CU(dmalloc(&c->halo_extra, MAX_HALOS));
+        CU(dmalloc(&c->n_limited, 1));
     }
     std::vector<HaloExtra> ex(c->nhalos);
     for (int j = 0; j < c->nhalos; j++) {
@@ -952,10 +1310,8 @@ extern "C" int tg_make_magnetic_field(tg_ctx *c, const tg_bfield *par, double *n
         ex[j].r_sample_dm = par->r_sample_dm ? par->r_sample_dm[j] : 0;
         ex[j].is_stripped = par->is_stripped ? par->is_stripped[j] : 0;
     }
-    HaloExtra *dex = nullptr;
-    int *dcnt = nullptr;
-    CU(dmalloc(&dex, c->nhalos));
-    CU(dmalloc(&dcnt, 1));
+    HaloExtra *dex = c->halo_extra;
+    int *dcnt = c->n_limited;
     CU(cudaMemcpyAsync(dex, ex.data(), sizeof(HaloExtra) * c->nhalos, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(dcnt, 0, sizeof(int), c->stream));
     int rc = reset_counters(c);
@@ -970,6 +1326,9 @@ extern "C" int tg_make_magnetic_field(tg_ctx *c, const tg_bfield *par, double *n
     CU(cudaEventRecord(c->ev[2], c->stream));
     if ((rc = launch_sweep<MODE_ROTA>(c, a))) return rc;
     CU(cudaEventRecord(c->ev[3], c->stream));
+    // every rank needs the whole field: its maximum is global (magnetic_field.c:77-86), and the
+    // cap below indexes Halo_containing by particle number
+    if ((rc = gather_slices(c, c->bfld, 3 * sizeof(float)))) return rc;
     const int nb = cdiv(n, RED_THREADS);
     k_bfld_max<<<nb, RED_THREADS, 0, c->stream>>>(n, c->bfld, c->partial);
     LAUNCH_CHECK();
@@ -977,7 +1336,7 @@ extern "C" int tg_make_magnetic_field(tg_ctx *c, const tg_bfield *par, double *n
     LAUNCH_CHECK();
     double max_b2 = 0;
     CU(cudaMemcpyAsync(&max_b2, c->scal + 3, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    if ((rc = check_flags(c))) return rc;        // (synchronises)
     const double norm = par->bfld_norm / sqrt(max_b2) / sqrt(3.0);     // magnetic_field.c:88-90
     k_bfld_normalise<<<cdiv(n, T), T, 0, c->stream>>>(n, c->pw, c->bfld, norm, c->box.boxhalf_f, c->halos, dex,
                                                      c->nhalos, par->sub_first, c->box.box_d,
@@ -986,10 +1345,7 @@ extern "C" int tg_make_magnetic_field(tg_ctx *c, const tg_bfield *par, double *n
     CU(cudaEventRecord(c->ev[1], c->stream));
     int cnt = 0;
     CU(cudaMemcpyAsync(&cnt, dcnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    rc = finish_stats(c, true);
-    cudaFree(dex);
-    cudaFree(dcnt);
-    if (rc) return rc;
+    if ((rc = finish_stats(c, true))) return rc;
     if (norm_out) *norm_out = norm;
     if (n_limited_out) *n_limited_out = cnt;
     return TG_OK;
@@ -998,6 +1354,7 @@ extern "C" int tg_make_magnetic_field(tg_ctx *c, const tg_bfield *par, double *n
 extern "C" int tg_get_apot(tg_ctx *c, float *apot)
 {
     if (!c || !apot) return TG_EINVAL;
+    TG_GROUP0(c, tg_get_apot(k, apot));
     if (!c->have_apot) return fail(c, TG_EINVAL, "tg_get_apot: Apot not set");
     CU(cudaSetDevice(c->cfg.device));
     CU(cudaMemcpyAsync(apot, c->apot, sizeof(float) * 3 * c->n, cudaMemcpyDeviceToHost, c->stream));
@@ -1008,6 +1365,19 @@ extern "C" int tg_get_apot(tg_ctx *c, float *apot)
 extern "C" int tg_get_stats(tg_ctx *c, tg_stats *out)
 {
     if (!c || !out) return TG_EINVAL;
+    if (!c->kids.empty()) {      // counters summed over the ranks, times = the slowest rank
+        tg_stats t = c->kids[0]->stats;
+        for (size_t r = 1; r < c->kids.size(); r++) {
+            const tg_stats &k = c->kids[r]->stats;
+            t.pair_evals += k.pair_evals; t.gathered += k.gathered; t.searches += k.searches;
+            t.hsml_iters += k.hsml_iters; t.kernels += k.kernels; t.handed_back += k.handed_back;
+            for (int q = 0; q < 5; q++) t.handback_why[q] += k.handback_why[q];
+            t.sweep_ms = std::max(t.sweep_ms, k.sweep_ms);
+            t.step_ms = std::max(t.step_ms, k.step_ms);
+        }
+        *out = t;
+        return TG_OK;
+    }
     *out = c->stats;
     return TG_OK;
 }
@@ -1018,6 +1388,7 @@ extern "C" int tg_download_soa(tg_ctx *c, float *pos, int32_t *perm, float *hsml
                                float *varhsml, float *rho_model, float *bfld)
 {
     if (!c) return TG_EINVAL;
+    TG_GROUP0(c, tg_download_soa(k, pos, perm, hsml, rho, varhsml, rho_model, bfld));   // state is replicated
     CU(cudaSetDevice(c->cfg.device));
     const int n = c->n;
     cudaStream_t st = c->stream;
@@ -1040,7 +1411,45 @@ extern "C" int tg_download(tg_ctx *c, void *P, size_t p_stride, void *SphP, size
 {
     if (!c || !P || !SphP || p_stride < 52 || s_stride < 48)
         return fail(c, TG_EINVAL, "tg_download: records too small for ParticleData / GasParticleData");
+    TG_GROUP(c, tg_download(k, P, p_stride, SphP, s_stride));     // every rank writes its own slice
     const int n = c->n;
+    if (c->have_raw && p_stride == c->raw_pstride && s_stride == c->raw_sstride) {
+        // device path: gather the resident records by the permutation, patch, one DMA each.
+        // With a communicator every rank does this for its slice [lo, hi) of the new order (so
+        // the copies to the host run in parallel on every GPU's PCIe link) and the slices of
+        // the new resident copy are all-gathered.
+        CU(cudaSetDevice(c->cfg.device));
+        cudaStream_t st = c->stream;
+        const int wp = (int)(p_stride / 4), ws = (int)(s_stride / 4);
+        const size_t lo = c->comm ? c->lo : 0, m = c->comm ? c->hi - c->lo : n;
+        const size_t tp = m * wp, ts = m * ws;
+        if (m) {
+            k_gather_records<<<cdiv((long long)tp, 256), 256, 0, st>>>(tp, wp, c->id + lo, (const uint32_t *)c->rawP,
+                                                                       (uint32_t *)(c->outP + lo * p_stride));
+            LAUNCH_CHECK();
+            k_gather_records<<<cdiv((long long)ts, 256), 256, 0, st>>>(ts, ws, c->id + lo, (const uint32_t *)c->rawS,
+                                                                       (uint32_t *)(c->outS + lo * s_stride));
+            LAUNCH_CHECK();
+            k_patch_records<<<cdiv((long long)m, 256), 256, 0, st>>>(
+                (int)m, (int)lo, c->outP + lo * p_stride, p_stride, c->outS + lo * s_stride, s_stride, c->posh + lo,
+                c->index_valid ? c->key_lo_s + lo : nullptr, c->key_hi_s + lo, c->rho + lo, c->varh + lo,
+                c->bfld + 3 * lo, c->rm_state + lo);
+            LAUNCH_CHECK();
+            CU(cudaMemcpyAsync((char *)P + lo * p_stride, c->outP + lo * p_stride, m * p_stride, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync((char *)SphP + lo * s_stride, c->outS + lo * s_stride, m * s_stride, cudaMemcpyDeviceToHost, st));
+        }
+        int rc;
+        if ((rc = gather_slices(c, c->outP, p_stride))) return rc;
+        if ((rc = gather_slices(c, c->outS, s_stride))) return rc;
+        // the records now ARE in the current order: they become the resident copy
+        std::swap(c->rawP, c->outP);
+        std::swap(c->rawS, c->outS);
+        k_iota<<<cdiv(n, 256), 256, 0, st>>>(n, c->id);
+        LAUNCH_CHECK();
+        CU(cudaStreamSynchronize(st));
+        return TG_OK;
+    }
+    // host path (state uploaded as plain arrays, records only on the host)
     std::vector<float> pos((size_t)3 * n), hsml(n), rho(n), varh(n), rhom(n), bfld((size_t)3 * n);
     std::vector<int32_t> perm(n);
     int rc = tg_download_soa(c, pos.data(), perm.data(), hsml.data(), rho.data(), varh.data(),
@@ -1088,6 +1497,7 @@ extern "C" int tg_download(tg_ctx *c, void *P, size_t p_stride, void *SphP, size
 extern "C" int tg_wvt_scratch(tg_ctx *c, float *hsml_wvt, float *delta)
 {
     if (!c) return TG_EINVAL;
+    TG_NOGROUP(c, "tg_wvt_scratch");
     CU(cudaSetDevice(c->cfg.device));
     const int n = c->n;
     CU(cudaStreamSynchronize(c->stream));
@@ -1113,6 +1523,7 @@ extern "C" int tg_wvt_scratch(tg_ctx *c, float *hsml_wvt, float *delta)
 extern "C" int tg_peano_keys(tg_ctx *c, uint64_t *hi, uint64_t *lo)
 {
     if (!c || !hi || !lo) return TG_EINVAL;
+    TG_NOGROUP(c, "tg_peano_keys");
     CU(cudaSetDevice(c->cfg.device));
     const int n = c->n;
     CU(cudaMemsetAsync(c->flags + 2, 0, sizeof(int), c->stream));
@@ -1128,6 +1539,7 @@ extern "C" int tg_peano_keys(tg_ctx *c, uint64_t *hi, uint64_t *lo)
 extern "C" int tg_sort(tg_ctx *c, int32_t *perm)
 {
     if (!c) return TG_EINVAL;
+    TG_GROUP(c, tg_sort(k, k->cfg.rank == 0 ? perm : nullptr));
     CU(cudaSetDevice(c->cfg.device));
     int rc = prepare_index(c);
     if (rc) return rc;
@@ -1142,16 +1554,16 @@ extern "C" int tg_sort(tg_ctx *c, int32_t *perm)
 extern "C" int tg_find_ngb(tg_ctx *c, int i, float h, int32_t *list, int *count)
 {
     if (!c || !list || !count || i < 0 || i >= c->n) return TG_EINVAL;
+    TG_GROUP0(c, tg_find_ngb(k, i, h, list, count));
     if (!c->index_valid) return fail(c, TG_EINVAL, "tg_find_ngb: no index");
     CU(cudaSetDevice(c->cfg.device));
-    int *d = nullptr;
-    CU(dmalloc(&d, TG_NGBMAX + 1));
+    if (!c->ngb_scratch) CU(dmalloc(&c->ngb_scratch, TG_NGBMAX + 1));
+    int *d = c->ngb_scratch;
     k_find_ngb<<<1, 32, 0, c->stream>>>(c->bvh, c->box, c->pw, i, h, c->defect.dmap, c->defect.nodes, d, d + TG_NGBMAX);
     c->launches++;
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = cudaMemcpy(count, d + TG_NGBMAX, sizeof(int), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(list, d, sizeof(int) * (*count), cudaMemcpyDeviceToHost);
-    cudaFree(d);
     if (e != cudaSuccess) return fail(c, TG_ECUDA, "tg_find_ngb: %s", cudaGetErrorString(e));
     return TG_OK;
 }
@@ -1159,6 +1571,7 @@ extern "C" int tg_find_ngb(tg_ctx *c, int i, float h, int32_t *list, int *count)
 extern "C" int tg_guess_hsml(tg_ctx *c, float *out)
 {
     if (!c || !out) return TG_EINVAL;
+    TG_GROUP0(c, tg_guess_hsml(k, out));
     if (!c->index_valid) return fail(c, TG_EINVAL, "tg_guess_hsml: no index");
     CU(cudaSetDevice(c->cfg.device));
     const int n = c->n, T = 256;
@@ -1178,6 +1591,7 @@ extern "C" int tg_guess_hsml(tg_ctx *c, float *out)
 extern "C" int tg_debug_tile_counts(tg_ctx *c, int *out, int *ntiles)
 {
     if (!c || !ntiles) return TG_EINVAL;
+    TG_NOGROUP(c, "tg_debug_tile_counts");
     CU(cudaSetDevice(c->cfg.device));
     *ntiles = c->bvh.lvl_n[0];
     if (out) {
@@ -1190,6 +1604,7 @@ extern "C" int tg_debug_tile_counts(tg_ctx *c, int *out, int *ntiles)
 extern "C" int tg_get_exchange(tg_ctx *c, tg_exchange *out)
 {
     if (!c || !out) return TG_EINVAL;
+    TG_NOGROUP(c, "tg_get_exchange");
     out->pos_hsml_dev = c->posh;
     out->rho_dev = c->rho;
     out->varhsml_dev = c->varh;

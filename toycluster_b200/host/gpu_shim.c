@@ -48,10 +48,14 @@ static void ensure_context(void)
     cfg.mpart_gas = Param.Mpart[0];
     cfg.mtotal = Param.Mtotal;
     cfg.flags = Shim_flags;
-    if (getenv("TOYGPU_FLAGS"))      /* e.g. 1 = TG_WVT_SEQUENTIAL, 2 = TG_EXACT_NEIGHBOURS */
+    if (getenv("TOYGPU_FLAGS"))      /* e.g. 1 = TG_WVT_SEQUENTIAL, 2 = TG_EXACT_NEIGHBOURS, 4 = TG_FAST */
         cfg.flags |= (unsigned)strtoul(getenv("TOYGPU_FLAGS"), NULL, 0);
     cfg.rank = 0;
     cfg.nranks = 1;
+    /* TOYGPU_NGPUS=8: this one process drives 8 devices; the library partitions the targets,
+     * exchanges the slices over NVLink (NCCL) and reduces the error statistics itself */
+    cfg.ngpus = getenv("TOYGPU_NGPUS") ? atoi(getenv("TOYGPU_NGPUS")) : 0;
+    cfg.devices = NULL;
 
     int rc = tg_create(&Ctx, &cfg);
     Assert(rc == TG_OK, "libtoygpu: tg_create failed (%d): %s", rc, tg_last_error(NULL));
@@ -69,6 +73,13 @@ static void ensure_context(void)
     }
     check(tg_set_halos(Ctx, Param.Nhalos, rows), "tg_set_halos");
     Free(rows);
+
+    /* P and SphP are allocated once by Setup() (setup.c:244-250) and cross the bus in every
+     * operator call: page-lock the gas range so those copies are DMA.  Best effort. */
+    if (!getenv("TOYGPU_NO_PIN")) {
+        (void)tg_pin_host(Ctx, P, (size_t)Param.Npart[0] * sizeof *P);
+        (void)tg_pin_host(Ctx, SphP, (size_t)Param.Npart[0] * sizeof *SphP);
+    }
 }
 
 void Find_sph_quantities()
