@@ -25,8 +25,13 @@
 extern "C" {
 #endif
 
+#ifdef TG_CUBIC_SPLINE   /* libtoygpu_m4.so == the reference built with -DSPH_CUBIC_SPLINE */
+#define TG_DESNNGB 50    /* globals.h:42 */
+#define TG_NGBMAX  400   /* globals.h:44 */
+#else
 #define TG_DESNNGB 295   /* globals.h:48 */
 #define TG_NGBMAX  2360  /* globals.h:50 */
+#endif
 #define TG_NUMITER 64    /* wvt_relax.c:7 */
 
 enum {
@@ -85,6 +90,10 @@ typedef struct {
                             group of rank contexts with their own NCCL communicators; every call
                             below then acts on all of them (rank/nranks must be 0/0 or 0/1) */
     const int *devices;  /* ngpus device ordinals, or NULL for 0 .. ngpus-1 */
+    double rho0_fac, rc_fac; /* Param.Rho0_Fac, Param.Rc_Fac of a -DDOUBLE_BETA_COOL_CORES build
+                            (setup.c:604-612): both > 0 => halos with tg_halo.cuspy get the second,
+                            cool-core beta component; both 0 => the default build, which ignores
+                            Have_Cuspy in Gas_density_profile */
 } tg_config;
 
 typedef struct tg_ctx tg_ctx;

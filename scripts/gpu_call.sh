@@ -1,5 +1,5 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_fast.py -x -q -k "not full_size" > gpurun_out/t_fast.log 2>&1; echo "rc=$?" >> gpurun_out/t_fast.log
-tail -15 gpurun_out/t_fast.log
-python scripts/time_variants.py > gpurun_out/variants.log 2>&1; cat gpurun_out/variants.log
-bash scripts/prof_round.sh r02b
+nvidia-smi -L
+timeout 2400 python -m pytest tests -q -m gpu > gpurun_out/t_all2.log 2>&1; echo "rc=$?" >> gpurun_out/t_all2.log
+tail -40 gpurun_out/t_all2.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 8 --warmup 3 > gpurun_out/b_fast2.json 2> gpurun_out/b_fast2.err; cat gpurun_out/b_fast2.json; tail -5 gpurun_out/b_fast2.err

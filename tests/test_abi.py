@@ -46,7 +46,7 @@ def test_struct_layouts_match_header(tmp_path):
     want = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     got = [ctypes.sizeof(c) for c in (api._Config, api.Stats, api._Halo, api._BField, api._Exchange)]
     assert got == want, (got, want)
-    assert want[0] == 72 and want[2] == 72
+    assert want[0] == 88 and want[2] == 72
 
 
 def test_no_cpu_fallback():

@@ -112,3 +112,67 @@ def test_gpu_driver_writes_the_same_gadget_file(tmp_path, mass_ratio, ntotal, ex
     bg = np.frombuffer(g["BFLD"], np.float32).reshape(-1, 3)
     scale = np.abs(bc).max(axis=1, keepdims=True) + 1e-30
     assert (np.abs(bg - bc) / scale).max() < 1e-5
+
+
+# ---- compile-time variants of the reference (Makefile:4-25) ---------------------------------
+# Each pair is the WHOLE reference program built with the option, once with its own hot path
+# and once with gpu_shim.c on libtoygpu (the cubic-spline pair links libtoygpu_m4.so, the
+# library built with -DTG_CUBIC_SPLINE).
+
+def _variant_pair(tmp_path, suffix, extra_par, ntotal=20000, mass_ratio=0.0):
+    cpu, gpu = CPU + suffix, GPU + suffix
+    if not (os.path.exists(cpu) and os.path.exists(gpu)):
+        pytest.skip(f"oracle/_ref drivers{suffix} not built (make -C oracle driver)")
+    for tag in ("c", "g"):
+        (tmp_path / f"{tag}.par").write_text(
+            PAR.format(out=f"IC_{tag}", ntotal=ntotal, mass_ratio=mass_ratio, bnorm="20e-6") + extra_par)
+    out_c = run(cpu, "c.par", tmp_path, {})
+    out_g = run(gpu, "g.par", tmp_path, {"TOYGPU_FLAGS": "1"})      # TG_WVT_SEQUENTIAL
+    it_c = [l for l in out_c.splitlines() if l.lstrip().startswith("#")]
+    it_g = [l for l in out_g.splitlines() if l.lstrip().startswith("#")]
+    assert len(it_c) >= 3 and it_c == it_g, (it_c[:3], it_g[:3])
+    c, g = read_gadget2(tmp_path / "IC_c"), read_gadget2(tmp_path / "IC_g")
+    assert list(c) == list(g)
+    for label in c:
+        if label == "BFLD":
+            bc = np.frombuffer(c["BFLD"], np.float32).reshape(-1, 3)
+            bg = np.frombuffer(g["BFLD"], np.float32).reshape(-1, 3)
+            scale = np.abs(bc).max(axis=1, keepdims=True) + 1e-30
+            assert (np.abs(bg - bc) / scale).max() < 1e-5
+        else:
+            assert c[label] == g[label], label
+    return out_c
+
+
+@pytest.mark.gpu
+def test_cubic_spline_build_writes_the_same_gadget_file(tmp_path):
+    """-DSPH_CUBIC_SPLINE (sph.c:140-146,201,442-466; globals.h:40-52; wvt_relax.c:48-49): M4
+    kernel, 50 neighbours, NGBMAX 400, no bias correction, VarHsmlFac = 1, step 0.035."""
+    out = _variant_pair(tmp_path, "_m4", "")
+    assert "step=0.035" in out
+
+
+@pytest.mark.gpu
+def test_cool_core_build_writes_the_same_gadget_file(tmp_path):
+    """-DDOUBLE_BETA_COOL_CORES (setup.c:604-612): halo 0 is cuspy (Cuspy bit 0) and gets the
+    second beta component rho0*Rho0_Fac / (1 + (r Rc_Fac / rc)^2) in Global_density_model."""
+    par = PAR.replace("Cuspy       0", "Cuspy       1") + "Rho0_Fac    50\nRc_Fac      40\n"
+    cpu, gpu = CPU + "_cc", GPU + "_cc"
+    if not (os.path.exists(cpu) and os.path.exists(gpu)):
+        pytest.skip("oracle/_ref drivers_cc not built (make -C oracle driver)")
+    for tag in ("c", "g"):
+        (tmp_path / f"{tag}.par").write_text(par.format(out=f"IC_{tag}", ntotal=20000, mass_ratio=0, bnorm="20e-6"))
+    out_c = run(cpu, "c.par", tmp_path, {})
+    out_g = run(gpu, "g.par", tmp_path, {"TOYGPU_FLAGS": "1"})
+    it_c = [l for l in out_c.splitlines() if l.lstrip().startswith("#")]
+    it_g = [l for l in out_g.splitlines() if l.lstrip().startswith("#")]
+    assert len(it_c) >= 3 and it_c == it_g
+    c, g = read_gadget2(tmp_path / "IC_c"), read_gadget2(tmp_path / "IC_g")
+    for label in c:
+        if label != "BFLD":
+            assert c[label] == g[label], label
+    # and the option really changed the model: the default build on the same file differs
+    (tmp_path / "d.par").write_text(par.format(out="IC_d", ntotal=20000, mass_ratio=0, bnorm="20e-6"))
+    run(CPU, "d.par", tmp_path, {})
+    d = read_gadget2(tmp_path / "IC_d")
+    assert d["RHOM"] != c["RHOM"]

@@ -46,7 +46,8 @@ class _Config(C.Structure):
     _fields_ = [("device", C.c_int), ("n_gas", C.c_int), ("boxsize", C.c_double),
                 ("mpart_gas", C.c_double), ("mtotal", C.c_double), ("flags", C.c_uint),
                 ("rank", C.c_int), ("nranks", C.c_int), ("stream", C.c_void_p),
-                ("ngpus", C.c_int), ("devices", C.POINTER(C.c_int))]
+                ("ngpus", C.c_int), ("devices", C.POINTER(C.c_int)),
+                ("rho0_fac", C.c_double), ("rc_fac", C.c_double)]
 
 
 class _BField(C.Structure):
@@ -159,14 +160,14 @@ class HotPath:
     """One device context == the global state the reference's path works on."""
 
     def __init__(self, n_gas, boxsize, mpart_gas, mtotal, halo_table, device=0, flags=0,
-                 rank=0, nranks=1, stream=None, ngpus=0, devices=None):
+                 rank=0, nranks=1, stream=None, ngpus=0, devices=None, rho0_fac=0.0, rc_fac=0.0):
         self.lib = load()
         self.n = int(n_gas)
         self._ctx = C.c_void_p()
         devs = (C.c_int * len(devices))(*devices) if devices else None
         cfg = _Config(int(device), self.n, float(boxsize), float(mpart_gas), float(mtotal),
                       int(flags), int(rank), int(nranks), C.c_void_p(stream or None),
-                      int(ngpus), devs)
+                      int(ngpus), devs, float(rho0_fac), float(rc_fac))
         rc = self.lib.tg_create(C.byref(self._ctx), C.byref(cfg))
         if rc != 0:
             msg = self.lib.tg_last_error(None).decode()

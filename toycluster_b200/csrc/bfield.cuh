@@ -13,7 +13,12 @@ static __device__ __forceinline__ double gas_density_profile(double r, const Hal
     const double q = r / h.rcore, s = r / h.rcut;
     const double base = __dadd_rn(1.0, __dmul_rn(q, q));
     const double cut = __dadd_rn(1.0, __dmul_rn(__dmul_rn(__dmul_rn(s, s), s), s));
-    return h.rho0 * pow(base, -3.0 / 2.0 * h.beta) / cut;
+    double rho = h.rho0 * pow(base, -3.0 / 2.0 * h.beta) / cut;
+    if (h.rho0_cc != 0) {                                       // setup.c:604-612
+        const double qc = r / h.rc_cc;
+        rho = __dadd_rn(rho, h.rho0_cc / __dadd_rn(1.0, __dmul_rn(qc, qc)) / cut);
+    }
+    return rho;
 }
 
 // magnetic_field.c:33-69.  pw = positions in the current (Peano) order.

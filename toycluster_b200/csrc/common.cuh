@@ -3,11 +3,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// -DTG_CUBIC_SPLINE builds the library the way -DSPH_CUBIC_SPLINE builds the reference
+// (Makefile:25): M4 kernel in Find_hsml (sph.c:140-146, 442-466), DESNNGB 50 and NGBMAX 400
+// (globals.h:40-52), no bias correction and no dRhodHsml (sph.c:201), WVT step 0.035
+// (wvt_relax.c:48-49).  It is a separate shared object, libtoygpu_m4.so.
+#ifdef TG_CUBIC_SPLINE
+#define TG_DESNNGB 50
+#define TG_NGBMAX 400
+#else
 #define TG_DESNNGB 295
 #define TG_NGBMAX 2360
+#endif
 #define FULL_MASK 0xffffffffu
 #define MAX_LEVELS 8
-#define MAX_HALOS 128
+#define MAX_HALOS 4096   // MAXHALOS, globals.h:58
 
 // globals.h:62-63 -- the reference's literal constants, not the exact values
 #define K_SQRT3 1.73205080756887719
@@ -18,6 +27,9 @@ struct Halo {            // one row of Global_density_model's table
     double cx, cy, cz;   // D_CoM; Boxsize/2 is subtracted at evaluation time (wvt_relax.c:240)
     double rho0, beta, rcore, rcut;
     double mass_gas;
+    // -DDOUBLE_BETA_COOL_CORES (setup.c:604-612): rho0 * Rho0_Fac and rcore / Rc_Fac of a cuspy
+    // halo; rho0_cc == 0 => no second beta component (the default build ignores Have_Cuspy)
+    double rho0_cc, rc_cc;
 };
 
 // Sorted-order bounding-box hierarchy over groups of 32 consecutive particles.

@@ -20,7 +20,12 @@ static __device__ __forceinline__ double halo_density(const Halo &h, double x, d
     // setup.c:601-602, product and sum kept un-contracted like the -std=c99 build
     const double base = __dadd_rn(1.0, __dmul_rn(q, q));
     const double cut = __dadd_rn(1.0, __dmul_rn(__dmul_rn(__dmul_rn(s, s), s), s));
-    return h.rho0 * pow(base, -3.0 / 2.0 * h.beta) / cut;
+    double rho = h.rho0 * pow(base, -3.0 / 2.0 * h.beta) / cut;
+    if (h.rho0_cc != 0) {                                       // setup.c:604-612
+        const double qc = r / h.rc_cc;
+        rho = __dadd_rn(rho, h.rho0_cc / __dadd_rn(1.0, __dmul_rn(qc, qc)) / cut);
+    }
+    return rho;
 }
 
 // The same profile in fast float arithmetic, good to ~1e-5: only used to decide WHICH halos
@@ -33,7 +38,12 @@ static __device__ __forceinline__ float halo_density_estimate(const Halo &h, flo
     const float r2 = dx * dx + dy * dy + dz * dz;
     const float rc = (float)h.rcore, rt = (float)h.rcut;
     const float s2 = r2 / (rt * rt);
-    return (float)h.rho0 * __powf(1.f + r2 / (rc * rc), -1.5f * (float)h.beta) / (1.f + s2 * s2);
+    float rho = (float)h.rho0 * __powf(1.f + r2 / (rc * rc), -1.5f * (float)h.beta) / (1.f + s2 * s2);
+    if (h.rho0_cc != 0) {
+        const float rcc = (float)h.rc_cc;
+        rho += (float)h.rho0_cc / (1.f + r2 / (rcc * rcc)) / (1.f + s2 * s2);
+    }
+    return rho;
 }
 
 static __device__ __forceinline__ float global_density_model(float xf, float yf, float zf,

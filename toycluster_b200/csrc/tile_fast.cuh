@@ -396,15 +396,20 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     if (use && u < 1.f) npair++;
                 }
             };
-            {   // the gather of the next batch is in flight while this one is evaluated
+            {   // the gather of the next batch is in flight while this one is evaluated (two batches
+                // per trip, so the hand-over needs no register moves)
+                const int kend = nU + lane;
                 int g0 = ul[lane];                       // (nU >= 1: the target itself is a hit)
                 float4 p0 = a.pw[g0];
-                for (int k = lane; k < nU + lane; k += 32) {
-                    const int kn = k + 32 < nU + lane ? k + 32 : k;  // (the last batch re-reads itself)
-                    const int g1 = ul[kn];
+                for (int k = lane; k < kend; k += 64) {
+                    const int k1 = k + 32 < kend ? k + 32 : k;       // (past the end: re-read, unused)
+                    const int g1 = ul[k1];
                     const float4 p1 = a.pw[g1];
                     batch(k, g0, p0, std::false_type{});
-                    g0 = g1; p0 = p1;
+                    const int k2 = k + 64 < kend ? k + 64 : k;
+                    g0 = ul[k2];
+                    p0 = a.pw[g0];
+                    if (k + 32 < kend) batch(k + 32, g1, p1, std::false_type{});
                 }
             }
             if (__any_sync(FULL_MASK, sawflag))

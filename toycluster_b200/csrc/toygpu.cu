@@ -261,6 +261,10 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
         return fail(c, TG_EINVAL, "tg_create: n_gas, boxsize and mpart_gas must be positive");
     if ((cfg->flags & TG_FAST) && (cfg->flags & TG_WVT_SEQUENTIAL))
         return fail(c, TG_EINVAL, "tg_create: TG_FAST and TG_WVT_SEQUENTIAL exclude each other");
+#ifdef TG_CUBIC_SPLINE
+    if (cfg->flags & TG_FAST)
+        return fail(c, TG_EINVAL, "tg_create: TG_FAST has WC6 polynomials only; the cubic-spline build has the exact modes");
+#endif
     if (cfg->ngpus > 1) {
         // group context: one rank context per device + one communicator each (ncclCommInitAll)
         NcclApi *api = nccl_api();
@@ -521,6 +525,8 @@ extern "C" int tg_set_halos(tg_ctx *c, int n, const tg_halo *h)
 {
     TG_GROUP(c, tg_set_halos(k, n, h));
     if (!c || n < 0 || n > MAX_HALOS || (n && !h)) return fail(c, TG_EINVAL, "tg_set_halos: bad arguments (max %d rows)", MAX_HALOS);
+    if (c->kids.empty() && (c->cfg.rho0_fac < 0 || c->cfg.rc_fac < 0 || (c->cfg.rho0_fac > 0) != (c->cfg.rc_fac > 0)))
+        return fail(c, TG_EINVAL, "tg_config: rho0_fac and rc_fac must both be positive (cool cores) or both 0");
     CU(cudaSetDevice(c->cfg.device));
     std::vector<Halo> rows(n);
     for (int i = 0; i < n; i++) {
@@ -528,6 +534,11 @@ extern "C" int tg_set_halos(tg_ctx *c, int n, const tg_halo *h)
         rows[i].rho0 = h[i].rho0; rows[i].beta = h[i].beta;
         rows[i].rcore = h[i].rcore; rows[i].rcut = h[i].rcut;
         rows[i].mass_gas = h[i].mass_gas;
+        // setup.c:604-612: only a -DDOUBLE_BETA_COOL_CORES build looks at Have_Cuspy; the caller
+        // says which build it stands in for by giving (or not giving) the two factors
+        const bool cc = h[i].cuspy && c->cfg.rho0_fac > 0 && c->cfg.rc_fac > 0;
+        rows[i].rho0_cc = cc ? h[i].rho0 * c->cfg.rho0_fac : 0.0;
+        rows[i].rc_cc = cc ? h[i].rcore / c->cfg.rc_fac : 1.0;
     }
     if (n) CU(cudaMemcpyAsync(c->halos, rows.data(), n * sizeof(Halo), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1217,8 +1228,12 @@ extern "C" int tg_regularise(tg_ctx *c, int max_iters, tg_log_fn log, void *user
                                   "all-reduce in between)");
     // wvt_relax.c:46-59
     int it = -1, started = 0;
+#ifdef TG_CUBIC_SPLINE
+    double step = 0.035;                                     // wvt_relax.c:48-49
+#else
     double step = 0.0085;
     if (c->cfg.mtotal < 1e5) step /= 2;
+#endif
     double errLast = DBL_MAX, errDiff = DBL_MAX, errDiffLast = DBL_MAX;
     int rc;
 

@@ -56,6 +56,10 @@ static void ensure_context(void)
      * exchanges the slices over NVLink (NCCL) and reduces the error statistics itself */
     cfg.ngpus = getenv("TOYGPU_NGPUS") ? atoi(getenv("TOYGPU_NGPUS")) : 0;
     cfg.devices = NULL;
+#ifdef DOUBLE_BETA_COOL_CORES                  /* Makefile:15; setup.c:604-612 */
+    cfg.rho0_fac = Param.Rho0_Fac;
+    cfg.rc_fac = Param.Rc_Fac;
+#endif
 
     int rc = tg_create(&Ctx, &cfg);
     Assert(rc == TG_OK, "libtoygpu: tg_create failed (%d): %s", rc, tg_last_error(NULL));
