@@ -210,6 +210,12 @@ typedef struct {
     const int *is_stripped;
 } tg_bfield;
 int tg_make_magnetic_field(tg_ctx *ctx, const tg_bfield *par, double *norm_out, int *n_limited_out);
+/* Reassign_particles_to_halos(), the per-particle half (positions.c:264-283):
+ * ids[k] = Halo_containing(gas, Pos_k - Boxsize/2) for the current state, npart[j] = particles
+ * of halo j (may be NULL).  Uses r_sample_gas, is_stripped and sub_first of `par`.  The index
+ * sort of the ids and the record permutation (positions.c:405-443) stay with the caller: the
+ * order of equal ids is whatever the reference's unstable gsl_heapsort_index makes of them. */
+int tg_halo_ids(tg_ctx *ctx, const tg_bfield *par, int32_t *ids, long long *npart);
 /* Apot of the current order, apot[n][3] (what tg_make_magnetic_field or tg_set_apot left). */
 int tg_get_apot(tg_ctx *ctx, float *apot);
 

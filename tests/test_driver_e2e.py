@@ -176,3 +176,24 @@ def test_cool_core_build_writes_the_same_gadget_file(tmp_path):
     run(CPU, "d.par", tmp_path, {})
     d = read_gadget2(tmp_path / "IC_d")
     assert d["RHOM"] != c["RHOM"]
+
+
+@pytest.mark.gpu
+def test_reassign_on_the_device_writes_the_same_gadget_file(tmp_path):
+    """Reassign_particles_to_halos() from the shim -- Halo_containing per particle on
+    the device (tg_halo_ids), the reference's own index heapsort on those ids -- leaves the
+    particle order of the Gadget file unchanged, two halos and all."""
+    gpu_r = GPU + "_r"
+    if not (os.path.exists(CPU) and os.path.exists(gpu_r)):
+        pytest.skip("oracle/_ref/Toycluster_gpu_r not built (make -C oracle driver)")
+    for tag in ("c", "g"):
+        (tmp_path / f"{tag}.par").write_text(PAR.format(out=f"IC_{tag}", ntotal=30000, mass_ratio=0.3125, bnorm="20e-6"))
+    out_c = run(CPU, "c.par", tmp_path, {})
+    out_g = run(gpu_r, "g.par", tmp_path, {"TOYGPU_FLAGS": "1"})
+    dist_c = [l for l in out_c.splitlines() if l.startswith("   Main ") or l.startswith("   Bullet ")]
+    dist_g = [l for l in out_g.splitlines() if l.startswith("   Main ") or l.startswith("   Bullet ")]
+    assert len(dist_c) >= 2 and dist_c == dist_g          # "Particle Distribution after Relaxation"
+    c, g = read_gadget2(tmp_path / "IC_c"), read_gadget2(tmp_path / "IC_g")
+    for label in c:
+        if label != "BFLD":
+            assert c[label] == g[label], label

@@ -85,7 +85,7 @@ EXPORTS = [
     "tg_bfld_from_rotA", "tg_wvt_iteration", "tg_wvt_begin", "tg_wvt_finish", "tg_wvt_scratch", "tg_get_stats", "tg_peano_keys",
     "tg_sort", "tg_find_ngb", "tg_guess_hsml", "tg_get_exchange",
     "tg_make_magnetic_field", "tg_get_apot", "tg_pin_host", "tg_unpin_host",
-    "tg_comm_id", "tg_comm_init",
+    "tg_comm_id", "tg_comm_init", "tg_halo_ids",
 ]
 
 _lib = None
@@ -146,6 +146,7 @@ def load():
     lib.tg_get_apot.argtypes = [C.c_void_p, C.c_void_p]
     lib.tg_pin_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.tg_unpin_host.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tg_halo_ids.argtypes = [C.c_void_p, C.POINTER(_BField), C.c_void_p, C.c_void_p]
     lib.tg_comm_id.argtypes = [C.c_void_p]
     lib.tg_comm_init.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib
@@ -315,6 +316,20 @@ class HotPath:
         norm, cnt = C.c_double(), C.c_int()
         self._check(self.lib.tg_make_magnetic_field(self._ctx, C.byref(par), C.byref(norm), C.byref(cnt)))
         return norm.value, cnt.value
+
+    def halo_ids(self, r_sample_gas, is_stripped=None, sub_first=None):
+        """positions.c:264-283: (haloID per gas particle, particles per halo) of the current state."""
+        nh = self.nhalos
+        gas = np.ascontiguousarray(r_sample_gas, np.float64)
+        dm = np.zeros(nh)
+        st = np.ascontiguousarray(np.zeros(nh) if is_stripped is None else is_stripped, np.int32)
+        par = _BField(0.0, 0.0, 0.0, 0.0, nh if sub_first is None else int(sub_first),
+                      gas.ctypes.data_as(C.POINTER(C.c_double)), dm.ctypes.data_as(C.POINTER(C.c_double)),
+                      st.ctypes.data_as(C.POINTER(C.c_int)))
+        ids = np.empty(self.n, np.int32)
+        cnt = np.zeros(nh, np.int64)
+        self._check(self.lib.tg_halo_ids(self._ctx, C.byref(par), _ptr(ids), _ptr(cnt)))
+        return ids, cnt
 
     def get_apot(self):
         out = np.empty((self.n, 3), np.float32)

@@ -131,3 +131,20 @@ __global__ void k_bfld_normalise(int n, const float4 *__restrict__ pw, float *__
     }
     bfld[3 * (size_t)k] = b0; bfld[3 * (size_t)k + 1] = b1; bfld[3 * (size_t)k + 2] = b2;
 }
+
+// positions.c:264-283: haloID of every gas particle (Halo_containing with type 0: the halo of
+// the largest gas density among those whose sampling radius holds the particle) and the
+// per-halo counts.  posh = current state (x, y, z, Hsml).
+__global__ void k_halo_ids(int n, const float4 *__restrict__ posh, float boxhalf_f,
+                           const Halo *__restrict__ halos, const HaloExtra *__restrict__ ex, int nhalos,
+                           int sub_first, double boxsize, int *__restrict__ ids,
+                           unsigned long long *__restrict__ counts)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 p = posh[k];
+    const int i = halo_containing(0, __fsub_rn(p.x, boxhalf_f), __fsub_rn(p.y, boxhalf_f),
+                                  __fsub_rn(p.z, boxhalf_f), halos, ex, nhalos, sub_first, boxsize);
+    ids[k] = i;
+    if (i >= 0) atomicAdd(&counts[i], 1ull);
+}

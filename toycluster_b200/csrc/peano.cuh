@@ -68,24 +68,6 @@ static __device__ __forceinline__ void peano_key(double x, double y, double z,
     lo = l << 2;
 }
 
-// Reversed key (peano.c:211-284): planes 20..62 pushed LSB-plane first, so plane 62 (tree
-// level 1) ends next to a zero level-0 triplet at the bottom.
-static __device__ __forceinline__ void reversed_peano_key(double x, double y, double z,
-                                                          uint64_t &hi, uint64_t &lo)
-{
-    const Transposed T = hilbert_transpose<20>(x, y, z);
-    uint64_t h = 0, l = 0;
-#pragma unroll 1
-    for (int plane = 20; plane <= 62; plane++) {
-        const uint64_t tri = (((T.a >> plane) & 1) << 2) | (((T.b >> plane) & 1) << 1) |
-                             ((T.c >> plane) & 1);
-        h = (h << 3) | (l >> 61);
-        l = (l << 3) | tri;
-    }
-    hi = (h << 3) | (l >> 61);
-    lo = l << 3;
-}
-
 // One thread per particle: keys of pos/Boxsize (peano.c:63-71). posh = (x, y, z, hsml).
 __global__ void k_peano_keys(int n, const float4 *__restrict__ posh, double box,
                              uint64_t *__restrict__ key_hi, uint64_t *__restrict__ key_lo,

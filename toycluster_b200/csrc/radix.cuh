@@ -208,6 +208,10 @@ k_radix_scatter(int n, const uint64_t *__restrict__ keys_in, const int *__restri
 // that agree in those bits by (key_hi, key_lo, index).  One thread per run start; runs are a
 // handful of particles at most (the sorted bits resolve cells of 2^-16 Boxsize or finer), so a
 // serial insertion sort is fine.  hi_sorted is permuted along with idx.
+// A run longer than RS_TIE_CAP (thousands of particles inside one 2^-16 Boxsize cell, or exact
+// duplicates) would make that O(L^2) on one thread: it is left alone and reported through
+// n_tied[1], which the step turns into an error instead of an apparent hang.
+#define RS_TIE_CAP 256
 __global__ void k_fix_ties(int n, uint64_t *__restrict__ hi_sorted, int *__restrict__ idx,
                            const uint64_t *__restrict__ key_lo, int low_bits, int *__restrict__ n_tied)
 {
@@ -219,6 +223,7 @@ __global__ void k_fix_ties(int n, uint64_t *__restrict__ hi_sorted, int *__restr
     int end = k + 1;
     while (end < n && (hi_sorted[end] >> low_bits) == h) end++;
     atomicAdd(n_tied, end - k);
+    if (end - k > RS_TIE_CAP) { atomicMax(n_tied + 1, end - k); return; }
     for (int a = k + 1; a < end; a++) {
         const int ia = idx[a];
         const uint64_t ha = hi_sorted[a], la = key_lo[ia];

@@ -96,7 +96,8 @@ struct tg_ctx {
     double *partial = nullptr;      // block partials
     int npartial = 0;
     double *scal = nullptr;         // [0] vsum, [1] err sum, [2] err max
-    int *flags = nullptr;           // [0] next, [1] status, [2] range_err, [3] n_tied, [4] cold, [5] nwork, [6] next (work list)
+    int *flags = nullptr;           // [0] next, [1] status, [2] range_err, [3] n_tied, [4] cold, [5] nwork, [6] next (work list),
+                                    // [7] stop (tg_regularise), [8] n_tied scratch, [9] longest unsorted tie run
     unsigned long long *counters = nullptr;   // 4
     double *gscratch = nullptr;
     int sweep_blocks = 0;
@@ -115,6 +116,7 @@ struct tg_ctx {
     HaloExtra *halo_extra = nullptr;   // tg_make_magnetic_field scratch
     int *n_limited = nullptr;
     int *ngb_scratch = nullptr;        // tg_find_ngb
+    unsigned long long *halo_counts = nullptr;   // tg_halo_ids
     ncclComm_t comm = nullptr;
     double *errbuf = nullptr;       // [3 * nranks] gathered (err sum, err max, stop flag)
     std::vector<tg_ctx *> kids;
@@ -237,6 +239,7 @@ extern "C" int tg_destroy(tg_ctx *c)
     if (c->halo_extra) cudaFree(c->halo_extra);
     if (c->n_limited) cudaFree(c->n_limited);
     if (c->ngb_scratch) cudaFree(c->ngb_scratch);
+    if (c->halo_counts) cudaFree(c->halo_counts);
     void *ptrs[] = {c->posh, c->id, c->apot, c->stage, c->key_hi, c->key_lo, c->key_tmp, c->idx, c->idx_tmp,
                     c->hist, c->pw, c->soa, c->hsml_in, c->rho_model, c->rm_state, c->rm_state_s, c->id_s, c->key_lo_s, c->apot_s,
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->sub_mem, c->cpl,
@@ -413,7 +416,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     CUC(dmalloc(&c->ev_count, n));
     CUC(dmalloc(&c->ev_start, n));
     CUC(dmalloc(&c->guess, n));
-    c->defect.cap_events = 4096;
+    c->defect.cap_events = std::max(4096, n / 4);
     c->defect.cap_nodes = std::max(1 << 20, n / 2);
     CUC(dmalloc(&c->defect.events, c->defect.cap_events));
     CUC(dmalloc(&c->defect.counts, 8));
@@ -426,9 +429,9 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     c->npartial = cdiv(n, RED_THREADS);
     CUC(dmalloc(&c->partial, (size_t)2 * c->npartial));
     CUC(dmalloc(&c->scal, 4));
-    CUC(dmalloc(&c->flags, 8));
+    CUC(dmalloc(&c->flags, 12));
     CUC(dmalloc(&c->counters, 12));
-    CUC(cudaMemsetAsync(c->flags, 0, 8 * sizeof(int), c->stream));
+    CUC(cudaMemsetAsync(c->flags, 0, 12 * sizeof(int), c->stream));
     CUC(cudaMemsetAsync(c->counters, 0, 12 * sizeof(unsigned long long), c->stream));
 
     // sweep grid: every SM full of resident blocks (persistent, work-stealing)
@@ -836,7 +839,8 @@ static int sort_keys(tg_ctx *c)
     }
     c->key_hi_s = kin;
     c->idx_s = iin;
-    k_fix_ties<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->idx_s, c->key_lo, low_bits, c->flags + 3);
+    CU(cudaMemsetAsync(c->flags + 8, 0, 2 * sizeof(int), c->stream));
+    k_fix_ties<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->idx_s, c->key_lo, low_bits, c->flags + 8);
     LAUNCH_CHECK();
     return TG_OK;
 }
@@ -992,9 +996,9 @@ template <int MODE> static int launch_sweep(tg_ctx *c, const SweepArgs &a)
     return launch_generic<MODE>(c, a);
 }
 
-static int check_flags(tg_ctx *c)
+static int check_flags(tg_ctx *c, bool swept = true)
 {
-    int f[4], dc[4];
+    int f[10], dc[4];
     {   // a rank that fails must take the others with it, or their next collective hangs
         const int rc = reduce_flags_max(c, c->flags + 1, 2);
         if (rc) return rc;
@@ -1005,7 +1009,14 @@ static int check_flags(tg_ctx *c)
     c->stats.displaced_nodes = dc[0];
     c->stats.displaced_particles = dc[3];
     c->stats.displaced_overflow = dc[2];
+    const int tie = f[9];
     if (f[2]) return fail(c, TG_ERANGE, "particle position outside [0, Boxsize] (peano.c:130-132)");
+    if (tie) return fail(c, TG_ERANGE, "%d particles share one sort cell (coincident positions?): the tie fix-up "
+                         "stops at runs of %d; rerun with TOYGPU_FULL_SORT=1 or remove the duplicates", tie, RS_TIE_CAP);
+    if (swept && dc[2] && !(c->cfg.flags & TG_EXACT_NEIGHBOURS))
+        return fail(c, TG_ERANGE, "more displaced reference-tree nodes than the path table holds (%d events): the "
+                         "neighbour sets would silently stop being the reference's; use TG_EXACT_NEIGHBOURS "
+                         "for the exact predicate sets", c->defect.cap_events);
     if (f[1]) return fail(c, TG_ENOCONV, "hsml iteration did not terminate (fewer than %d gas particles in reach?)", TG_DESNNGB);
     return TG_OK;
 }
@@ -1366,6 +1377,41 @@ extern "C" int tg_make_magnetic_field(tg_ctx *c, const tg_bfield *par, double *n
     return TG_OK;
 }
 
+// Reassign_particles_to_halos(), the per-particle half (positions.c:264-283).
+// The sort that follows it in the reference (positions.c:405-443) is gsl_heapsort_index on the
+// ids, whose order of EQUAL ids decides the particle order of the output file; it stays with
+// the caller (the shim runs the reference's own Qsort_Index on these ids).
+extern "C" int tg_halo_ids(tg_ctx *c, const tg_bfield *par, int32_t *ids, long long *npart)
+{
+    if (!c || !par || !ids) return fail(c, TG_EINVAL, "tg_halo_ids: null argument");
+    TG_GROUP0(c, tg_halo_ids(k, par, ids, npart));        // the state is replicated on every rank
+    if (c->nhalos == 0) return fail(c, TG_EINVAL, "tg_set_halos has not been called");
+    CU(cudaSetDevice(c->cfg.device));
+    const int n = c->n, T = 256;
+    if (!c->halo_extra) {
+        CU(dmalloc(&c->halo_extra, MAX_HALOS));
+        CU(dmalloc(&c->n_limited, 1));
+    }
+    if (!c->halo_counts) CU(dmalloc(&c->halo_counts, MAX_HALOS));
+    std::vector<HaloExtra> ex(c->nhalos);
+    for (int j = 0; j < c->nhalos; j++) {
+        ex[j].r_sample_gas = par->r_sample_gas ? par->r_sample_gas[j] : 0;
+        ex[j].r_sample_dm = par->r_sample_dm ? par->r_sample_dm[j] : 0;
+        ex[j].is_stripped = par->is_stripped ? par->is_stripped[j] : 0;
+    }
+    CU(cudaMemcpyAsync(c->halo_extra, ex.data(), sizeof(HaloExtra) * c->nhalos, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->halo_counts, 0, sizeof(unsigned long long) * c->nhalos, c->stream));
+    k_halo_ids<<<cdiv(n, T), T, 0, c->stream>>>(n, c->posh, c->box.boxhalf_f, c->halos, c->halo_extra, c->nhalos,
+                                               par->sub_first, c->box.box_d, c->idx, c->halo_counts);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(ids, c->idx, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<unsigned long long> cnt(c->nhalos);
+    CU(cudaMemcpyAsync(cnt.data(), c->halo_counts, sizeof(unsigned long long) * c->nhalos, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (npart) for (int j = 0; j < c->nhalos; j++) npart[j] = (long long)cnt[j];
+    return TG_OK;
+}
+
 extern "C" int tg_get_apot(tg_ctx *c, float *apot)
 {
     if (!c || !apot) return TG_EINVAL;
@@ -1548,7 +1594,7 @@ extern "C" int tg_peano_keys(tg_ctx *c, uint64_t *hi, uint64_t *lo)
     CU(cudaMemcpyAsync(hi, c->key_hi, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(lo, c->key_lo, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
     c->index_valid = false;
-    return check_flags(c);
+    return check_flags(c, false);
 }
 
 extern "C" int tg_sort(tg_ctx *c, int32_t *perm)
@@ -1561,7 +1607,7 @@ extern "C" int tg_sort(tg_ctx *c, int32_t *perm)
     // positions and Hsml unchanged: carry them into the new order
     k_carry<<<cdiv(c->n, 256), 256, 0, c->stream>>>(0, c->n, c->pw, c->hsml_in, c->posh);
     LAUNCH_CHECK();
-    if ((rc = check_flags(c))) return rc;
+    if ((rc = check_flags(c, false))) return rc;
     if (perm) CU(cudaMemcpy(perm, c->id, sizeof(int) * c->n, cudaMemcpyDeviceToHost));
     return TG_OK;
 }

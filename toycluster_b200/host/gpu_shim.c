@@ -199,6 +199,93 @@ void Make_magnetic_field()
 }
 #endif
 
+#ifdef TOYGPU_SHIM_REASSIGN
+/* positions.c:264-324.  With this defined the shim also replaces
+ * Reassign_particles_to_halos (positions.c is then compiled with
+ * -DReassign_particles_to_halos=<unused name>, see oracle/Makefile): the per-particle
+ * Halo_containing -- an FP64 pow per halo and particle, serial in the reference -- runs on the
+ * device over the positions it already holds.  The index sort of the ids is the reference's own
+ * Qsort_Index (sort.c:185-195 -> gsl_heapsort_index): its order of equal ids is what the Gadget
+ * file's particle order is made of, so it is not replaced; the permutation and the bookkeeping
+ * below restate positions.c:285-323, 405-443. */
+int compare_int(const void *a, const void *b);        /* positions.c:391 */
+
+void Reassign_particles_to_halos()
+{
+    ensure_context();
+    const int n = Param.Npart[0], nh = Param.Nhalos;
+    int *haloID = Malloc((size_t)n * sizeof *haloID);
+    long long *npart = Malloc(nh * sizeof *npart);
+    double *rs_gas = Malloc(nh * sizeof *rs_gas);
+    int *stripped = Malloc(nh * sizeof *stripped);
+    for (int j = 0; j < nh; j++) {
+        rs_gas[j] = Halo[j].R_Sample[0];
+        stripped[j] = Halo[j].Is_Stripped;
+    }
+    tg_bfield par;
+    memset(&par, 0, sizeof par);
+    par.sub_first = Sub.First;
+    par.r_sample_gas = rs_gas;
+    par.is_stripped = stripped;
+    /* the device state is the one Find_sph_quantities / Make_magnetic_field left: same order
+     * and positions as P[] */
+    check(tg_halo_ids(Ctx, &par, haloID, npart), "tg_halo_ids");
+
+    /* sort_particles(), positions.c:405-443 */
+    size_t *idx = Malloc((size_t)n * sizeof *idx);
+    Qsort_Index(Omp.NThreads, idx, haloID, n, sizeof *haloID, &compare_int);
+    for (size_t i = 0; i < (size_t)n; i++) {
+        if (idx[i] == i)
+            continue;
+        size_t dest = i;
+        struct ParticleData Ptmp = P[dest];
+        struct GasParticleData SphPtmp = SphP[dest];
+        size_t src = idx[i];
+        for (;;) {
+            memcpy(&P[dest], &P[src], sizeof *P);
+            memcpy(&SphP[dest], &SphP[src], sizeof *SphP);
+            idx[dest] = dest;
+            dest = src;
+            src = idx[dest];
+            if (src == i)
+                break;
+        }
+        memcpy(&P[dest], &Ptmp, sizeof *P);
+        memcpy(&SphP[dest], &SphPtmp, sizeof *SphP);
+        idx[dest] = dest;
+    }
+    Free(idx); Free(haloID);
+
+    /* positions.c:289-323 */
+    Sub.Ntotal = Sub.Npart[1];
+    Sub.Npart[0] = 0;
+    for (int i = 0; i < nh; i++) {
+        Halo[i].Npart[0] = npart[i];
+        Halo[i].Ntotal = Halo[i].Npart[0] + Halo[i].Npart[1];
+        if (i >= Sub.First) {
+            Sub.Ntotal += npart[i];
+            Sub.Npart[0] += npart[i];
+        }
+    }
+    int iGas = Halo[0].Npart[0];
+    for (int i = 1; i < nh; i++) {
+        Halo[i].Gas = &(P[iGas]);
+        Halo[i].SphP = &(SphP[iGas]);
+        iGas += Halo[i].Npart[0];
+    }
+    printf("Particle Distribution after Relaxation :\n"
+           "   Main     %8lld   %8lld   %8lld  \n",
+           Halo[0].Ntotal, Halo[0].Npart[0], Halo[0].Npart[1]);
+    if (Param.Mass_Ratio)
+        printf("   Bullet   %8lld   %8lld   %8lld  \n",
+               Halo[1].Ntotal, Halo[1].Npart[0], Halo[1].Npart[1]);
+#ifdef SUBSTRUCTURE
+    printf("   Subhalos %8d   %8d   %8d \n", Sub.Ntotal, Sub.Npart[0], Sub.Npart[1]);
+#endif
+    Free(npart); Free(rs_gas); Free(stripped);
+}
+#endif
+
 /* wvt_relax.c:227-256; host-side, for callers outside the path (proto.h:46). */
 float Global_density_model(const int ipart)
 {
