@@ -266,6 +266,9 @@ def test_gpu_lattice_input_overflows_the_event_table_loudly():
     g.upload(pos)
     with pytest.raises(tc.ToyGpuError, match="displaced reference-tree nodes"):
         g.find_sph_quantities()
+    with pytest.raises(tc.ToyGpuError, match="upload the particles again"):
+        g.find_sph_quantities()                           # ids and positions disagree after a failure
+    g.upload(pos)
     assert g.sort() is not None                           # sorting alone does not need the paths
     e = tc.HotPath.from_workload(w, flags=tc.EXACT_NEIGHBOURS)
     e.upload(pos)

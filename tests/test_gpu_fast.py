@@ -226,3 +226,38 @@ def test_full_size_merger_1e6_all_modes():
     g = tc.HotPath.from_workload(w, flags=tc.FAST)
     for it in range(2):
         _check_iteration(w, g, start[it], after[it], steps[it], it, cold=it == 0)
+
+
+def test_fast_rot_a_on_the_tile_path():
+    """Bfld_from_rotA_SPH (sph.c:216-300) in TG_FAST runs on the tile sweep (one search at Hsml,
+    float addends, FP64 tree over the lanes): within 1e-5 of the field scale of the reference."""
+    w = workloads.make("merger_1e6", n_gas=40000, seed=2)
+    r = _ref(w)
+    r.load(w.pos)
+    r.find_sph_quantities()
+    r.find_sph_quantities()
+    s = r.read()
+    apot = np.repeat(np.sqrt(s["rho"] / s["rho"].max())[:, None], 3, 1).astype(np.float32)   # (Rho_Model is
+    apot[:, 1] *= 0.5                                                # only set by the WVT loop)
+    apot[:, 2] *= 0.25
+    assert np.isfinite(apot).all()
+    r.set_apot(apot)
+    r.bfld_from_rotA()
+    want = r.read()["bfld"]
+
+    g = tc.HotPath.from_workload(w, flags=tc.FAST)
+    g.upload(w.pos)
+    g.find_sph_quantities()
+    g.find_sph_quantities()
+    o = g.download()
+    assert np.array_equal(o["id"], s["id"])
+    g.set_apot(apot)
+    g.bfld_from_rotA_sph()
+    st = g.stats()
+    assert st["handed_back"] < 0.6 * w.n_gas, st            # the tile path ran
+    got = g.download(bfld=True)["bfld"]
+    scale = np.abs(want).max()
+    err = np.abs(got.astype(np.float64) - want).max(axis=1) / scale
+    assert err.max() <= 1e-5, err.max()
+    rel = np.linalg.norm(got.astype(np.float64) - want, axis=1) / np.maximum(np.linalg.norm(want, axis=1), 1e-30)
+    assert np.quantile(rel, 0.99) <= 1e-4, np.quantile(rel, 0.99)

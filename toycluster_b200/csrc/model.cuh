@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 k_reorder_model(int n, const int *__restrict__ idx, const float4 *__restrict__ posh_in,
                 const int *__restrict__ id_in, const uint64_t *__restrict__ key_lo_in,
                 const float *__restrict__ apot_in, const float *__restrict__ rmstate_in,
-                float *__restrict__ rmstate_out, float4 *__restrict__ pw, float *__restrict__ soa,
+                float *__restrict__ rmstate_out, float4 *__restrict__ pw, float *__restrict__ pwp, float *__restrict__ soa,
                 float *__restrict__ hsml, int *__restrict__ id_out,
                 float *__restrict__ rho_model, uint64_t *__restrict__ key_lo_out,
                 float *__restrict__ apot_out,
@@ -135,6 +135,10 @@ k_reorder_model(int n, const int *__restrict__ idx, const float4 *__restrict__ p
         // wvt_relax.c:115: hsml = pow(WVTNNGB * Mpart / rho / fourpithird, 1/3) -> float
         const float hw = (float)pow(TG_DESNNGB * mpart / (double)rm / K_FOURPITHIRD, 1. / 3.);
         pw[k] = make_float4(p.x, p.y, p.z, hw);
+        {   // pair-interleaved copy: {x0, x1, y0, y1}, {z0, z1, w0, w1} per pair of particles
+            float *q = pwp + 8 * (size_t)(k >> 1) + (k & 1);
+            q[0] = p.x; q[2] = p.y; q[4] = p.z; q[6] = hw;
+        }
         const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
         soa[k] = p.x; soa[n8 + k] = p.y; soa[2 * n8 + k] = p.z;
         hsml[k] = p.w;
@@ -155,6 +159,9 @@ k_reorder_model(int n, const int *__restrict__ idx, const float4 *__restrict__ p
         const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
         const float qnan = __int_as_float(0x7fc00000);
         soa[k] = qnan; soa[n8 + k] = qnan; soa[2 * n8 + k] = qnan;
+        float *q = pwp + 8 * (size_t)(k >> 1) + (k & 1);
+        q[0] = qnan; q[2] = qnan; q[4] = qnan; q[6] = 0.f;
+        pw[k] = make_float4(qnan, qnan, qnan, 0.f);          // pw has n8 entries: the pad is addressable
     }
     const double s = block_sum(cube, sm);
     if (threadIdx.x == 0) partial[blockIdx.x] = s;

@@ -99,8 +99,10 @@ static __device__ __forceinline__ float box_box_dist2(float ax, float ay, float 
 }
 
 // Largest search radius target i can need on the fast path.
-static __device__ __forceinline__ float tile_radius(float hA, float hw_raw, float norm, double box)
+// rmode 1: one search at Hsml itself (rot A, sph.c:229).
+static __device__ __forceinline__ float tile_radius(float hA, float hw_raw, float norm, double box, int rmode = 0)
 {
+    if (rmode == 1) return hA;
     const float hB = (float)((double)hA * 1.23);                   // sph.c:51
     const float hsw = (float)((double)__fmul_rn(fabsf(hw_raw), norm) * box);   // wvt_relax.c:124,135
     return fmaxf(hB, hsw);
@@ -122,7 +124,7 @@ static __device__ __forceinline__ float tile_radius(float hA, float hw_raw, floa
 __global__ void __launch_bounds__(TW_WARPS * 32)
 k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw, const float *__restrict__ hsml_in,
             const double *__restrict__ vsum, int tile_lo, int tile_hi, int *__restrict__ tile_ng,
-            int *__restrict__ tile_groups)
+            int *__restrict__ tile_groups, int rmode)
 {
     __shared__ int s_queue[TW_WARPS][2][TW_QCAP];
     const int wib = threadIdx.x >> 5;
@@ -138,7 +140,7 @@ k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw, const float *__restric
     if (i < t.n) {
         const float hA = hsml_in[i];
         cold = hA == 0;
-        R = tile_radius(hA, pw[i].w, norm, bx.box_d);
+        R = tile_radius(hA, pw[i].w, norm, bx.box_d, rmode);
     }
     R = fmaxf(R, __shfl_xor_sync(FULL_MASK, R, 1));
     R = fmaxf(R, __shfl_xor_sync(FULL_MASK, R, 2));
@@ -146,7 +148,7 @@ k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw, const float *__restric
     const float Rsub = R;                       // max over this lane's run of 8 targets
     R = fmaxf(R, __shfl_xor_sync(FULL_MASK, R, 8));
     R = fmaxf(R, __shfl_xor_sync(FULL_MASK, R, 16));
-    if (__any_sync(FULL_MASK, cold) || !(R < bx.boxhalf_f)) {
+    if (__any_sync(FULL_MASK, cold) || !(R < 0.98f * bx.boxhalf_f)) {     // (0.49 Boxsize: tile_fast.cuh's wrap)
         if (lane == 0) tile_ng[tile] = -1;
         return;
     }

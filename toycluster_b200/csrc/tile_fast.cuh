@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
             if (i < n) {
                 const float4 pi = a.pw[i];
                 xi = pi.x; yi = pi.y; zi = pi.z;
-                const float R = tile_radius(a.hsml_in[i], pi.w, norm, a.bx.box_d);
+                const float R = tile_radius(a.hsml_in[i], pi.w, norm, a.bx.box_d, (MODE & MODE_ROTA) ? 1 : 0);
                 R2 = __fmul_rn(R, R);
             }
             const size_t n8 = ((size_t)n + 7) & ~(size_t)7;      // stride of the SoA copy
@@ -285,14 +285,22 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
             //     the words lane, lane+32, ... of the row and writes their hits to one contiguous
             //     stretch (order inside the list is irrelevant: all sums below are trees); uniform,
             //     fully unrolled bit loop with predicated stores (tile.cuh).
+            //     PAIRS (density / displacement modes): the list holds PAIRS of consecutive particles
+            //     (2p, 2p+1) with at least one hit -- the hot loop below evaluates both halves at once
+            //     with packed FP32 instructions on the pair-interleaved copy of the positions; the
+            //     half that is no hit fails the exact predicate by itself.  Half the bits to visit.
+            constexpr bool PAIRS = !(MODE & MODE_ROTA);
             constexpr int NW = TL_WORDS / 32;
             unsigned wd[NW];
-            int c = 0;
+            int c = 0, chits = 0;
 #pragma unroll
             for (int j = 0; j < NW; j++) {
                 const int q = j * 32 + lane;
-                wd[j] = q < ng ? s_mask[q * TL_MSTRIDE + tsel] : 0u;
-                c += __popc(wd[j]);
+                unsigned word = q < ng ? s_mask[q * TL_MSTRIDE + tsel] : 0u;
+                chits += __popc(word);
+                if (PAIRS) word = (word | (word >> 1)) & 0x55555555u;
+                wd[j] = word;
+                c += __popc(word);
             }
             int incl = c;
 #pragma unroll
@@ -301,7 +309,8 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 if (lane >= o) incl += v;
             }
             const int nU = __shfl_sync(FULL_MASK, incl, 31);
-            if (nU > TL_UCAP) { hand_back(i, 1); continue; }
+            // the separation list must hold every hit: the same bound as in tile.cuh
+            if ((PAIRS ? __reduce_add_sync(FULL_MASK, chits) : nU) > TL_UCAP) { hand_back(i, 1); continue; }
             {
                 int *out = ul + (incl - c);
 #pragma unroll
@@ -309,21 +318,38 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     if (j * 32 >= ng) break;               // warp-uniform
                     const unsigned word = wd[j];
                     const int4 rs = *(const int4 *)(s_run + 4 * (j * 32 + lane));   // the word's four runs
+                    if (PAIRS) {
 #pragma unroll
-                    for (int b = 0; b < 32; b++) {
-                        const int first = b < 8 ? rs.x : (b < 16 ? rs.y : (b < 24 ? rs.z : rs.w));
-                        if (word & (1u << b)) *out++ = first + (b & 7);
+                        for (int b = 0; b < 16; b++) {     // pair b of the word: run b / 4, pair b % 4 of it
+                            const int first = b < 4 ? rs.x : (b < 8 ? rs.y : (b < 12 ? rs.z : rs.w));
+                            if (word & (1u << (2 * b))) *out++ = (first >> 1) + (b & 3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 32; b++) {
+                            const int first = b < 8 ? rs.x : (b < 16 ? rs.y : (b < 24 ? rs.z : rs.w));
+                            if (word & (1u << b)) *out++ = first + (b & 7);
+                        }
                     }
                 }
-                // pad the last batch with the target itself, marked dead by the loop below
-                if (nU + lane < ((nU + 31) & ~31)) ul[nU + lane] = i;
+                // pad the last batch with the target itself (its pair), marked dead by the loop below
+                if (nU + lane < ((nU + 31) & ~31)) ul[nU + lane] = PAIRS ? i >> 1 : i;
             }
             __syncwarp();
 
             float4 pi = a.pw[i];
             pi.w = fabsf(pi.w);                    // the sign bit is the displaced-node flag
             float hA2, hB2, hsw2, Afy, cn;
-            {
+            float ax_i = 0, ay_i = 0, az_i = 0, inv_h = 0;        // rot(A): Apot_i, 1/Hsml
+            if (MODE & MODE_ROTA) {
+                const float hA = a.hsml_in[i];
+                hA2 = __fmul_rn(hA, hA); hB2 = hA2; hsw2 = 0; cn = 0;
+                inv_h = __frcp_rn(hA);
+                const float h2 = hA * hA;
+                // sph.c:278-280: weight = -m / rho_i * W'(r, h) / r * VarHsmlFac, W' = kW / h^4 * -22 (...)
+                Afy = (float)(-a.bx.mpart / (double)a.rho_in[i] * (double)a.varh_in[i] * (TF_KW * -22.0) / ((double)h2 * (double)h2));
+                ax_i = a.apot[3 * (size_t)i]; ay_i = a.apot[3 * (size_t)i + 1]; az_i = a.apot[3 * (size_t)i + 2];
+            } else {
                 const float hA = a.hsml_in[i];
                 const float hB = (float)((double)hA * 1.23);                      // sph.c:51
                 const float hi_w = __fmul_rn(pi.w, norm);                         // wvt_relax.c:124
@@ -381,6 +407,24 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     baseB -= __popc(mBo);
                 }
                 cntW += inW;
+                if (MODE & MODE_ROTA) {
+                    // sph.c:236-295: B_i += weight * (d x (A_i - A_j)) over Find_ngb_tree(i, Hsml_i)
+                    const float u = fminf(r * inv_h, 1.f);
+                    const float t = 1.f - u, t2 = t * t, t3 = t2 * t, t4 = t2 * t2;
+                    const float Q = fmaf(fmaf(16.f, u, 7.f), u, 1.f);
+                    const bool use = inA && gidx != i;                           // sph.c:247 skips i itself
+                    const float f = use ? (t4 * t3) * u * Q * (Afy * y) : 0.f;    // weight (dwk / r folded in)
+                    const float dX = __int_as_float(__float_as_int(ax) ^ (__float_as_int(dx) & 0x80000000));
+                    const float dY = __int_as_float(__float_as_int(ay) ^ (__float_as_int(dy) & 0x80000000));
+                    const float dZ = __int_as_float(__float_as_int(az) ^ (__float_as_int(dz) & 0x80000000));
+                    const float dAx = ax_i - a.apot[3 * (size_t)gidx], dAy = ay_i - a.apot[3 * (size_t)gidx + 1],
+                                dAz = az_i - a.apot[3 * (size_t)gidx + 2];
+                    sx = fmaf(f, dZ * dAy - dY * dAz, sx);
+                    sy = fmaf(f, dX * dAz - dZ * dAx, sy);
+                    sz = fmaf(f, dY * dAx - dX * dAy, sz);
+                    if (use) npair++;
+                    cntW += inA;                                                 // gathered: the Hsml set
+                }
                 if (MODE & MODE_WVT) {
                     // wvt_relax.c:137-170; nU <= TL_CAP < NGBMAX: the list cut cannot bite
                     const float hp = (pi.w + fabsf(pj.w)) * cn;                   // :158, length units
@@ -396,13 +440,113 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     if (use && u < 1.f) npair++;
                 }
             };
-            {   // the gather of the next batch is in flight while this one is evaluated (two batches
+            // Two particles per lane: pair p = particles (2p, 2p+1) from the pair-interleaved copy
+            // A = {x0, x1, y0, y1}, B = {z0, z1, w0, w1}; every float step below is one packed
+            // instruction for both (each half an ordinary IEEE operation, f32x2.cuh).
+            const f32x2 xi2 = pack2(pi.x, pi.x), yi2 = pack2(pi.y, pi.y), zi2 = pack2(pi.z, pi.z);
+            f32x2 sx2 = pack2(0.f, 0.f), sy2 = sx2, sz2 = sx2;
+            auto batch2 = [&](const int k, const int pidx, const ulonglong2 A, const ulonglong2 B) {
+                f32x2 dx2 = sub2(xi2, A.x), dy2 = sub2(yi2, A.y), dz2 = sub2(zi2, B.x);
+                if (!interior) {
+                    // closest image: d - Boxsize * rint(d / Boxsize) -- one rounded subtraction, the
+                    // value of tree.c:70-78 up to its sign; rint can only differ from the reference's
+                    // compare for |d| within 1e-7 of Boxsize/2, which is no hit for either image
+                    // (the tile walk only admits R < 0.49 Boxsize)
+                    const float ibox = 1.f / box;
+                    const f32x2 ib2 = pack2(ibox, ibox), mg2 = pack2(12582912.f, 12582912.f), nb2 = pack2(-box, -box);
+                    dx2 = fma2(sub2(fma2(dx2, ib2, mg2), mg2), nb2, dx2);
+                    dy2 = fma2(sub2(fma2(dy2, ib2, mg2), mg2), nb2, dy2);
+                    dz2 = fma2(sub2(fma2(dz2, ib2, mg2), mg2), nb2, dz2);
+                }
+                // tree.c:88 without FMA: packed products, SCALAR sums (ptxas would contract a packed
+                // product feeding a packed add into one FFMA2)
+                float px0, px1, py0, py1, pz0, pz1, w0, w1;
+                unpack2(mul2(dx2, dx2), px0, px1);
+                unpack2(mul2(dy2, dy2), py0, py1);
+                unpack2(mul2(dz2, dz2), pz0, pz1);
+                unpack2(B.y, w0, w1);
+                float r20 = __fadd_rn(__fadd_rn(px0, py0), pz0), r21 = __fadd_rn(__fadd_rn(px1, py1), pz1);
+                const bool live = k < nU;
+                const bool fl0 = df_flagged(w0), fl1 = df_flagged(w1);
+                r20 = (live && !fl0) ? r20 : 3.0e38f;       // dead: the pad, hits of the second pass;
+                r21 = (live && !fl1) ? r21 : 3.0e38f;       // (the NaN pad of an odd n compares false)
+                sawflag |= live && (fl0 | fl1);
+                const bool inA0 = r20 < hA2, inB0 = r20 < hB2, inW0 = r20 < hsw2;
+                const bool inA1 = r21 < hA2, inB1 = r21 < hB2, inW1 = r21 < hsw2;
+                // r = sqrt(r2): MUFU.RSQ and one Newton step
+                const float y0 = rsqrt_approx(fmaxf(r20, 1e-35f)), y1 = rsqrt_approx(fmaxf(r21, 1e-35f));
+                const f32x2 y2 = pack2(y0, y1), r2v = pack2(r20, r21);
+                f32x2 rr = mul2(r2v, y2);
+                rr = fma2(mul2(y2, pack2(0.5f, 0.5f)), fma2(sub2(pack2(0.f, 0.f), rr), rr, r2v), rr);
+                float r0, r1;
+                unpack2(rr, r0, r1);
+                if (MODE & MODE_DENSITY) {
+                    const unsigned mA0 = __ballot_sync(FULL_MASK, inA0), mA1 = __ballot_sync(FULL_MASK, inA1);
+                    const unsigned mBo0 = __ballot_sync(FULL_MASK, inB0) & ~mA0;
+                    const unsigned mBo1 = __ballot_sync(FULL_MASK, inB1) & ~mA1;
+                    const int nA0 = __popc(mA0), nB0 = __popc(mBo0);
+                    const int rank0 = __popc((inA0 ? mA0 : mBo0) & lt), rank1 = __popc((inA1 ? mA1 : mBo1) & lt);
+                    if (inB0) rl[inA0 ? cntA + rank0 : baseB - rank0] = r0;
+                    if (inB1) rl[inA1 ? cntA + nA0 + rank1 : baseB - nB0 - rank1] = r1;
+                    cntA += nA0 + __popc(mA1);
+                    baseB -= nB0 + __popc(mBo1);
+                }
+                cntW += inW0 + inW1;
+                if (MODE & MODE_WVT) {
+                    // wvt_relax.c:137-170, both halves at once
+                    const f32x2 aw2 = B.y & 0x7fffffff7fffffffull;                // |w|: sign = defect flag
+                    const f32x2 hp2 = mul2(add2(pack2(pi.w, pi.w), aw2), pack2(cn, cn));   // :158, length units
+                    float h0, h1, u0, u1;
+                    unpack2(hp2, h0, h1);
+                    unpack2(mul2(rr, pack2(rcp_approx(h0), rcp_approx(h1))), u0, u1);
+                    const f32x2 u = pack2(fminf(u0, 1.f), fminf(u1, 1.f));        // :160 skip <=> W = 0
+                    const f32x2 one2 = pack2(1.f, 1.f);
+                    const f32x2 t = sub2(one2, u), t2 = mul2(t, t), t4 = mul2(t2, t2);
+                    const f32x2 P = fma2(fma2(fma2(pack2(32.f, 32.f), u, pack2(25.f, 25.f)), u, pack2(8.f, 8.f)), u, one2);
+                    float f0, f1;
+                    unpack2(mul2(mul2(mul2(t4, t4), P), mul2(pack2(Afy, Afy), y2)), f0, f1);
+                    const bool use0 = inW0 && 2 * pidx != i, use1 = inW1 && 2 * pidx + 1 != i;   // :141
+                    const f32x2 f2 = pack2(use0 ? f0 : 0.f, use1 ? f1 : 0.f);
+                    sx2 = fma2(f2, dx2, sx2);
+                    sy2 = fma2(f2, dy2, sy2);
+                    sz2 = fma2(f2, dz2, sz2);
+                    if (use0 && fminf(u0, 1.f) < 1.f) npair++;
+                    if (use1 && fminf(u1, 1.f) < 1.f) npair++;
+                }
+            };
+            if (PAIRS) {
+                // the gather of the next batch is in flight while this one is evaluated (two batches
                 // per trip, so the hand-over needs no register moves)
+                const ulonglong2 *pp = (const ulonglong2 *)a.pwp;
                 const int kend = nU + lane;
                 int g0 = ul[lane];                       // (nU >= 1: the target itself is a hit)
-                float4 p0 = a.pw[g0];
+                ulonglong2 A0 = pp[2 * (size_t)g0], B0 = pp[2 * (size_t)g0 + 1];
                 for (int k = lane; k < kend; k += 64) {
                     const int k1 = k + 32 < kend ? k + 32 : k;       // (past the end: re-read, unused)
+                    const int g1 = ul[k1];
+                    const ulonglong2 A1 = pp[2 * (size_t)g1], B1 = pp[2 * (size_t)g1 + 1];
+                    batch2(k, g0, A0, B0);
+                    const int k2 = k + 64 < kend ? k + 64 : k;
+                    g0 = ul[k2];
+                    A0 = pp[2 * (size_t)g0]; B0 = pp[2 * (size_t)g0 + 1];
+                    if (k + 32 < kend) batch2(k + 32, g1, A1, B1);
+                }
+                float a0, a1;
+                unpack2(sx2, a0, a1); sx = a0 + a1;
+                unpack2(sy2, a0, a1); sy = a0 + a1;
+                unpack2(sz2, a0, a1); sz = a0 + a1;
+                if (__any_sync(FULL_MASK, sawflag))      // the flagged halves, one at a time
+                    for (int k = lane; k < nU + lane; k += 32) {
+                        const int g = 2 * ul[k];
+                        batch(k, g, a.pw[g], std::true_type{});
+                        batch(k, g + 1, a.pw[g + 1], std::true_type{});
+                    }
+            } else {
+                const int kend = nU + lane;
+                int g0 = ul[lane];
+                float4 p0 = a.pw[g0];
+                for (int k = lane; k < kend; k += 64) {
+                    const int k1 = k + 32 < kend ? k + 32 : k;
                     const int g1 = ul[k1];
                     const float4 p1 = a.pw[g1];
                     batch(k, g0, p0, std::false_type{});
@@ -411,12 +555,12 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     p0 = a.pw[g0];
                     if (k + 32 < kend) batch(k + 32, g1, p1, std::false_type{});
                 }
+                if (__any_sync(FULL_MASK, sawflag))
+                    for (int k = lane; k < nU + lane; k += 32) {
+                        const int g = ul[k];
+                        batch(k, g, a.pw[g], std::true_type{});
+                    }
             }
-            if (__any_sync(FULL_MASK, sawflag))
-                for (int k = lane; k < nU + lane; k += 32) {
-                    const int g = ul[k];
-                    batch(k, g, a.pw[g], std::true_type{});
-                }
             const int cntBo = TL_CAP - 1 - baseB;
             cntW = __reduce_add_sync(FULL_MASK, cntW);
             __syncwarp();
@@ -458,6 +602,16 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
 
             // (4) results
             double dsx = 0, dsy = 0, dsz = 0;
+            if (MODE & MODE_ROTA) {
+                dsx = warp_sum((double)sx); dsy = warp_sum((double)sy); dsz = warp_sum((double)sz);
+                npair = __reduce_add_sync(FULL_MASK, npair);
+                n_search = 1;
+                if (lane == 0) {
+                    a.bfld[3 * (size_t)i] = (float)dsx;
+                    a.bfld[3 * (size_t)i + 1] = (float)dsy;
+                    a.bfld[3 * (size_t)i + 2] = (float)dsz;
+                }
+            }
             if (MODE & MODE_WVT) {
                 dsx = warp_sum((double)sx); dsy = warp_sum((double)sy); dsz = warp_sum((double)sz);
                 npair = __reduce_add_sync(FULL_MASK, npair);

@@ -56,6 +56,7 @@ struct tg_ctx {
     bool have_apot = false;
     bool any_cold = true;
     bool index_valid = false;
+    bool poisoned = false;          // a step failed half-way: ids and positions disagree until the next upload
 
     // sort
     uint64_t *key_hi = nullptr, *key_lo = nullptr, *key_tmp = nullptr;
@@ -67,6 +68,7 @@ struct tg_ctx {
 
     // sorted
     float4 *pw = nullptr;
+    float *pwp = nullptr;           // pair-interleaved copy of pw (tile_fast.cuh)
     float *soa = nullptr;           // x[n8], y[n8], z[n8] copy of pw for the tile sweep's phase 1
     float *hsml_in = nullptr, *rho_model = nullptr;
     float *rm_state = nullptr, *rm_state_s = nullptr;   // SphP.Rho_Model as the driver sees it (current order)
@@ -241,7 +243,7 @@ extern "C" int tg_destroy(tg_ctx *c)
     if (c->ngb_scratch) cudaFree(c->ngb_scratch);
     if (c->halo_counts) cudaFree(c->halo_counts);
     void *ptrs[] = {c->posh, c->id, c->apot, c->stage, c->key_hi, c->key_lo, c->key_tmp, c->idx, c->idx_tmp,
-                    c->hist, c->pw, c->soa, c->hsml_in, c->rho_model, c->rm_state, c->rm_state_s, c->id_s, c->key_lo_s, c->apot_s,
+                    c->hist, c->pw, c->pwp, c->soa, c->hsml_in, c->rho_model, c->rm_state, c->rm_state_s, c->id_s, c->key_lo_s, c->apot_s,
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->sub_mem, c->cpl,
                     c->ev_level, c->ev_count, c->ev_start, c->guess, c->halos, c->partial, c->scal,
                     c->flags, c->counters, c->gscratch, c->tile_ng, c->tile_groups, c->worklist,
@@ -365,7 +367,8 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     CUC(dmalloc(&c->idx_tmp, n));
     c->ntiles = cdiv(n, RS_TILE);
     CUC(dmalloc(&c->hist, (size_t)RS_BINS * c->ntiles + RS_BINS));   // + digit totals
-    CUC(dmalloc(&c->pw, n));
+    CUC(dmalloc(&c->pw, ((size_t)n + 7) & ~(size_t)7));
+    CUC(dmalloc(&c->pwp, 4 * (((size_t)n + 7) & ~(size_t)7)));
     CUC(dmalloc(&c->soa, 3 * (((size_t)n + 7) & ~(size_t)7)));
     CUC(dmalloc(&c->hsml_in, n));
     CUC(dmalloc(&c->rho_model, n));
@@ -450,6 +453,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
         CUC(set((const void *)k_sweep<MODE_WVT_SEQ, false>));
         CUC(set((const void *)k_sweep<MODE_DENSITY | MODE_WVT, false>));
         CUC(set((const void *)k_sweep<MODE_ROTA, false>));
+        CUC(set((const void *)k_sweep<MODE_ROTA, true>));
         CUC(set((const void *)k_sweep<MODE_DENSITY, true>));
         CUC(set((const void *)k_sweep<MODE_WVT, true>));
         CUC(set((const void *)k_sweep<MODE_DENSITY | MODE_WVT, true>));
@@ -478,6 +482,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
         };
         CUC(set((const void *)k_sweep_tile_fast<MODE_DENSITY>));
         CUC(set((const void *)k_sweep_tile_fast<MODE_DENSITY | MODE_WVT>));
+        CUC(set((const void *)k_sweep_tile_fast<MODE_ROTA>));
         int per = 1;
         CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_sweep_tile_fast<MODE_DENSITY | MODE_WVT>,
                                                           TF_WARPS * 32, TF_SMEM));
@@ -569,6 +574,7 @@ static int upload_common(tg_ctx *c, const float *pos, const float *hsml)
     CU(cudaStreamSynchronize(c->stream));
     c->any_cold = cold != 0;
     c->index_valid = false;
+    c->poisoned = false;
     c->have_apot = false;
     c->have_raw = false;
     CU(cudaMemsetAsync(c->rm_state, 0, sizeof(float) * n, c->stream));
@@ -618,6 +624,7 @@ extern "C" int tg_upload_soa_slice(tg_ctx *c, const float *pos, const float *hsm
     CU(cudaStreamSynchronize(c->stream));
     c->any_cold = cold != 0;
     c->index_valid = false;
+    c->poisoned = false;
     c->have_apot = false;
     c->have_raw = false;
     CU(cudaMemsetAsync(c->rm_state, 0, sizeof(float) * n, c->stream));
@@ -776,6 +783,7 @@ extern "C" int tg_upload(tg_ctx *c, const void *P, size_t p_stride, const void *
     CU(cudaStreamSynchronize(c->stream));
     c->any_cold = cold != 0;
     c->index_valid = false;
+    c->poisoned = false;
     c->have_apot = with_apot;
     c->have_raw = true;
     return TG_OK;
@@ -850,12 +858,13 @@ static int prepare_index(tg_ctx *c)
 {
     const int n = c->n, T = 256;
     if (c->nhalos == 0) return fail(c, TG_EINVAL, "tg_set_halos has not been called");
+    if (c->poisoned) return fail(c, TG_EINVAL, "the previous step failed half-way: upload the particles again");
     int rc = sort_keys(c);
     if (rc) return rc;
 
     k_reorder_model<<<c->npartial, RED_THREADS, 0, c->stream>>>(
         n, c->idx_s, c->posh, c->id, c->key_lo, c->have_apot ? c->apot : nullptr, c->rm_state,
-        c->rm_state_s, c->pw, c->soa, c->hsml_in,
+        c->rm_state_s, c->pw, c->pwp, c->soa, c->hsml_in,
         c->id_s, c->rho_model, c->key_lo_s, c->apot_s, c->halos, c->nhalos, c->box.mpart,
         c->box.boxhalf_d, c->partial);
     LAUNCH_CHECK();
@@ -919,6 +928,7 @@ static SweepArgs sweep_args(tg_ctx *c, double step)
     a.bx = c->box;
     a.pw = c->pw;
     a.soa = c->soa;
+    a.pwp = (const float4 *)c->pwp;
     a.hsml_in = c->hsml_in;
     a.guess = c->guess;
     a.hsml_out = c->hsml_out;
@@ -967,17 +977,20 @@ template <int MODE> static int launch_tiled(tg_ctx *c, SweepArgs a)
     CU(cudaMemsetAsync(c->flags, 0, sizeof(int), c->stream));
     CU(cudaMemsetAsync(c->flags + 5, 0, 2 * sizeof(int), c->stream));
     k_tile_walk<<<cdiv(tile_hi - tile_lo, TW_WARPS), TW_WARPS * 32, 0, c->stream>>>(
-        c->bvh, c->box, c->pw, c->hsml_in, c->scal, tile_lo, tile_hi, c->tile_ng, c->tile_groups);
+        c->bvh, c->box, c->pw, a.hsml_in, c->scal, tile_lo, tile_hi, c->tile_ng, c->tile_groups,
+        MODE == MODE_ROTA ? 1 : 0);
     LAUNCH_CHECK();
     a.next = c->flags;
-    constexpr bool has_fast = MODE == MODE_DENSITY || MODE == (MODE_DENSITY | MODE_WVT);
+    constexpr bool has_fast = MODE == MODE_DENSITY || MODE == (MODE_DENSITY | MODE_WVT) || MODE == MODE_ROTA;
+    constexpr bool has_exact = MODE != MODE_ROTA;
     bool fast = false;
     if constexpr (has_fast) fast = (c->cfg.flags & TG_FAST) != 0;
     if (fast) {
         if constexpr (has_fast)
             k_sweep_tile_fast<MODE><<<c->fast_blocks, TF_WARPS * 32, TF_SMEM, c->stream>>>(a, tile_lo, tile_hi);
     } else {
-        k_sweep_tile<MODE><<<c->tile_blocks, TL_WARPS * 32, TL_SMEM, c->stream>>>(a, tile_lo, tile_hi);
+        if constexpr (has_exact)
+            k_sweep_tile<MODE><<<c->tile_blocks, TL_WARPS * 32, TL_SMEM, c->stream>>>(a, tile_lo, tile_hi);
     }
     LAUNCH_CHECK();
     a.next = c->flags + 6;
@@ -992,6 +1005,9 @@ template <int MODE> static int launch_sweep(tg_ctx *c, const SweepArgs &a)
                               MODE == (MODE_DENSITY | MODE_WVT);
     if constexpr (tileable) {
         if (c->use_tiles && !c->any_cold) return launch_tiled<MODE>(c, a);
+    }
+    if constexpr (MODE == MODE_ROTA) {       // rot(A) has a tile path in TG_FAST only
+        if (c->use_tiles && !c->any_cold && (c->cfg.flags & TG_FAST)) return launch_tiled<MODE>(c, a);
     }
     return launch_generic<MODE>(c, a);
 }
@@ -1010,6 +1026,12 @@ static int check_flags(tg_ctx *c, bool swept = true)
     c->stats.displaced_particles = dc[3];
     c->stats.displaced_overflow = dc[2];
     const int tie = f[9];
+    // the index build has already put the ids into the new order while the positions are only
+    // rewritten after a successful sweep: after any of the failures below the two disagree
+    if (f[2] || f[1] || tie || (swept && dc[2] && !(c->cfg.flags & TG_EXACT_NEIGHBOURS))) {
+        c->poisoned = true;
+        c->index_valid = false;
+    }
     if (f[2]) return fail(c, TG_ERANGE, "particle position outside [0, Boxsize] (peano.c:130-132)");
     if (tie) return fail(c, TG_ERANGE, "%d particles share one sort cell (coincident positions?): the tie fix-up "
                          "stops at runs of %d; rerun with TOYGPU_FULL_SORT=1 or remove the duplicates", tie, RS_TIE_CAP);
@@ -1136,6 +1158,7 @@ extern "C" int tg_find_sph_quantities(tg_ctx *c)
 extern "C" int tg_wvt_begin(tg_ctx *c, double step_guess, double *err_sum, double *err_max, int *count)
 {
     if (!c) return TG_EINVAL;
+    if (!(step_guess > 0)) return fail(c, TG_EINVAL, "tg_wvt_begin: step must be positive");
     if (!c->kids.empty()) {      // every rank returns the same global numbers
         const int rc = group_run(c, [&](tg_ctx *k) {
             double s = 0, m = 0; int cnt = 0;
