@@ -196,39 +196,45 @@ k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw, const float *__restric
         return;
     }
 
-    // ---- level-0 boxes: run against run, two boxes per pass (one per half warp) ---------
-    // lane & 15 = (tile run a, candidate run b): a = bits 2-3, b = bits 0-1
-    const int ra = (lane >> 2) & 3, rb = lane & 3, half = lane >> 4;
-    const int sa = 4 * tile + ra;
-    const float tx = t.scx[sa], ty = t.scy[sa], tz = t.scz[sa];
-    const float thx = t.shx[sa], thy = t.shy[sa], thz = t.shz[sa];
-    const float Ra = __shfl_sync(FULL_MASK, Rsub, ra * 8);
-    const float Ra2 = Ra * Ra * 1.00001f;
+    // ---- level-0 boxes: run against run, EIGHT boxes per pass ---------------------------
+    // lane = (candidate box c = lane / 4 of the pass, its run b = lane % 4); every lane holds the
+    // tile's own four sub-boxes (each with the largest radius of its 8 targets) in registers and
+    // tests its candidate run against all four, so a pass is one round of independent loads for
+    // eight boxes (it was one per two boxes: ~50 dependent L2 round trips per tile).
+    const int cb = lane >> 2, rb = lane & 3;
+    float tcx[4], tcy[4], tcz[4], thx[4], thy[4], thz[4], Ra2[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int sa = 4 * tile + q;
+        tcx[q] = t.scx[sa]; tcy[q] = t.scy[sa]; tcz[q] = t.scz[sa];
+        thx[q] = t.shx[sa]; thy[q] = t.shy[sa]; thz[q] = t.shz[sa];
+        const float Ra = __shfl_sync(FULL_MASK, Rsub, q * 8);
+        Ra2[q] = Ra * Ra * 1.00001f;
+    }
     int ng = 0, nruns = 0;
     int *out = tile_groups + (size_t)tile * TL_ENT;
-#pragma unroll 4
-    for (int j = 0; j < ncur; j += 2) {
-        const bool have = j + half < ncur;
-        const int g = have ? cur[j + half] : 0;
+    for (int j = 0; j < ncur; j += 8) {
+        const bool have = j + cb < ncur;
+        const int g = have ? cur[j + cb] : 0;
         const int sb = 4 * g + rb;
-        const bool near = have &&
-            box_box_dist2(tx, ty, tz, thx, thy, thz, t.scx[sb], t.scy[sb], t.scz[sb], t.shx[sb],
-                          t.shy[sb], t.shz[sb], bx.box_f, bx.boxhalf_f) <= Ra2;
+        const float bx_ = t.scx[sb], by_ = t.scy[sb], bz_ = t.scz[sb];
+        const float bhx = t.shx[sb], bhy = t.shy[sb], bhz = t.shz[sb];
+        bool near = false;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            near |= box_box_dist2(tcx[q], tcy[q], tcz[q], thx[q], thy[q], thz[q], bx_, by_, bz_, bhx, bhy, bhz,
+                                  bx.box_f, bx.boxhalf_f) <= Ra2[q];
+        near &= have;
         const unsigned m = __ballot_sync(FULL_MASK, near);
-        const unsigned lo16 = m & 0xffffu, hi16 = m >> 16;
-        const unsigned m0 = (lo16 | (lo16 >> 4) | (lo16 >> 8) | (lo16 >> 12)) & 0xfu;
-        const unsigned m1 = (hi16 | (hi16 >> 4) | (hi16 >> 8) | (hi16 >> 12)) & 0xfu;
-        const int g0 = __shfl_sync(FULL_MASK, g, 0), g1 = __shfl_sync(FULL_MASK, g, 16);
-        if (m0) {
-            if (ng < TL_ENT && lane == 0) out[ng] = (g0 << 4) | (int)m0;
-            ng++;
-            nruns += __popc(m0);
+        // boxes of the pass with at least one run in reach, in ascending order
+        unsigned nz = (m | (m >> 1) | (m >> 2) | (m >> 3)) & 0x11111111u;      // bit 4c: box c has a run
+        const int mine = (int)((m >> (4 * cb)) & 0xfu);
+        if (rb == 0 && mine) {
+            const int pos = ng + __popc(nz & ((1u << (4 * cb)) - 1u));
+            if (pos < TL_ENT) out[pos] = (g << 4) | mine;
         }
-        if (m1) {
-            if (ng < TL_ENT && lane == 0) out[ng] = (g1 << 4) | (int)m1;
-            ng++;
-            nruns += __popc(m1);
-        }
+        ng += __popc(nz);
+        nruns += __popc(m);
     }
     if (lane == 0) {
         if (ng > TL_ENT || nruns > TL_RUNS) tile_ng[tile] = -max(nruns, 2);
