@@ -260,8 +260,9 @@ def main():
     def one_step(step):
         if flush is not None:
             flush.zero_()
-        g.wvt_iteration(step)          # sort, index, sweep, error statistics, move, exchange
-        return g.stats()
+        g.wvt_begin(step)              # sort, index, sweep, error statistics (global when multi-rank)
+        g.wvt_finish(step)             # move + exchange of the moved slices: one pass of
+        return g.stats()               # wvt_relax.c:66-214 exactly as tg_regularise runs it
 
     pos_np0 = w.pos.copy()
 

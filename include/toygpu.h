@@ -190,6 +190,11 @@ int tg_wvt_iteration(tg_ctx *ctx, double step, double *err_max, double *err_mean
  * reference's `break`: positions stay, the new Hsml is kept. */
 int tg_wvt_begin(tg_ctx *ctx, double step_guess, double *err_sum, double *err_max, int *count);
 int tg_wvt_finish(tg_ctx *ctx, double step_final);
+/* With a communicator tg_wvt_finish exchanges the moved (x, y, z, Hsml) slices only; Rho and
+ * VarHsmlFac of the other ranks' slices are not needed by the next iteration.  This collective
+ * brings them in (tg_regularise and tg_wvt_iteration end with it; call it yourself before a
+ * download when you drive begin / finish).  No-op on one GPU. */
+int tg_sync_results(tg_ctx *ctx);
 /* Scratch of the last iteration (wvt_relax.c:36-44), in that iteration's Peano order. */
 int tg_wvt_scratch(tg_ctx *ctx, float *hsml_wvt, float *delta /* [n][3] */);
 

@@ -85,7 +85,7 @@ EXPORTS = [
     "tg_bfld_from_rotA", "tg_wvt_iteration", "tg_wvt_begin", "tg_wvt_finish", "tg_wvt_scratch", "tg_get_stats", "tg_peano_keys",
     "tg_sort", "tg_find_ngb", "tg_guess_hsml", "tg_get_exchange",
     "tg_make_magnetic_field", "tg_get_apot", "tg_pin_host", "tg_unpin_host",
-    "tg_comm_id", "tg_comm_init", "tg_halo_ids",
+    "tg_comm_id", "tg_comm_init", "tg_halo_ids", "tg_sync_results",
 ]
 
 _lib = None
@@ -134,6 +134,7 @@ def load():
     lib.tg_wvt_begin.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double),
                                  C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.tg_wvt_finish.argtypes = [C.c_void_p, C.c_double]
+    lib.tg_sync_results.argtypes = [C.c_void_p]
     lib.tg_wvt_scratch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tg_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.tg_peano_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -351,6 +352,10 @@ class HotPath:
 
     def wvt_finish(self, step_final):
         self._check(self.lib.tg_wvt_finish(self._ctx, float(step_final)))
+
+    def sync_results(self):
+        """Multi-rank: gather Rho / VarHsmlFac of every slice (after wvt_begin / wvt_finish)."""
+        self._check(self.lib.tg_sync_results(self._ctx))
 
     def wvt_scratch(self):
         h = np.empty(self.n, np.float32)

@@ -56,6 +56,7 @@ struct tg_ctx {
     bool have_apot = false;
     bool any_cold = true;
     bool index_valid = false;
+    bool density_stale = false;     // multi-rank: Rho / VarHsmlFac of the other slices not gathered yet
     bool poisoned = false;          // a step failed half-way: ids and positions disagree until the next upload
 
     // sort
@@ -1163,6 +1164,7 @@ extern "C" int tg_find_sph_quantities(tg_ctx *c)
     CU(cudaEventRecord(c->ev[3], c->stream));
     if ((rc = carry_state(c))) return rc;
     if ((rc = gather_state(c, true))) return rc;
+    c->density_stale = false;
     CU(cudaEventRecord(c->ev[1], c->stream));
     if ((rc = check_flags(c))) return rc;
     return finish_stats(c, true);
@@ -1245,9 +1247,29 @@ extern "C" int tg_wvt_finish(tg_ctx *c, double step_final)
         }
         if ((rc = move_pass(c, scale))) return rc;
     }
-    if ((rc = gather_state(c, true))) return rc;
+    // The moved slices travel every iteration; Rho / VarHsmlFac of the other ranks' slices are
+    // not needed by the next iteration and follow when the operator returns (tg_sync_results).
+    if ((rc = gather_state(c, false))) return rc;
+    c->density_stale = c->comm != nullptr;
     CU(cudaEventRecord(c->ev[1], c->stream));
     return finish_stats(c, true);
+}
+
+// Multi-rank: make Rho / VarHsmlFac of every slice present on every rank (collective; a no-op
+// when they already are).  tg_regularise, tg_wvt_iteration and tg_find_sph_quantities end with
+// it; hosts that drive tg_wvt_begin / tg_wvt_finish themselves call it before a download.
+extern "C" int tg_sync_results(tg_ctx *c)
+{
+    if (!c) return TG_EINVAL;
+    TG_GROUP(c, tg_sync_results(k));
+    if (!c->comm || !c->density_stale) return TG_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = gather_slices(c, c->rho, sizeof(float));
+    if (rc) return rc;
+    if ((rc = gather_slices(c, c->varh, sizeof(float)))) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    c->density_stale = false;
+    return TG_OK;
 }
 
 extern "C" int tg_wvt_iteration(tg_ctx *c, double step, double *err_max, double *err_mean)
@@ -1258,7 +1280,8 @@ extern "C" int tg_wvt_iteration(tg_ctx *c, double step, double *err_max, double 
     if (rc) return rc;
     if (err_max) *err_max = mx;
     if (err_mean) *err_mean = cnt > 0 ? sum / cnt : 0;
-    return tg_wvt_finish(c, step);
+    if ((rc = tg_wvt_finish(c, step))) return rc;
+    return tg_sync_results(c);
 }
 
 extern "C" int tg_regularise(tg_ctx *c, int max_iters, tg_log_fn log, void *user, int *iters_done)
@@ -1318,7 +1341,7 @@ extern "C" int tg_regularise(tg_ctx *c, int max_iters, tg_log_fn log, void *user
         if ((rc = tg_wvt_finish(c, step))) return rc;        // wvt_relax.c:108-214
     }
     if (iters_done) *iters_done = started;
-    return TG_OK;
+    return tg_sync_results(c);
 }
 
 extern "C" int tg_bfld_from_rotA(tg_ctx *c)
