@@ -5,7 +5,7 @@ import toycluster_b200 as tc
 from toycluster_b200 import workloads
 name = sys.argv[1] if len(sys.argv) > 1 else "merger_1e7"
 w = workloads.make(name)
-g = tc.HotPath.from_workload(w)
+g = tc.HotPath.from_workload(w, flags=tc.FAST)
 g.upload(w.pos)
 for it in range(4):
     g.wvt_iteration(0.0085)

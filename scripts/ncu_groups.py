@@ -1,7 +1,7 @@
 """Group the per-line output of ncu_lines.py by code region of tile_fast.cuh: ncu_groups.py lines.txt <inst per 1%>"""
 import re, collections, sys
 per = float(sys.argv[2]) if len(sys.argv) > 2 else 42.0
-src = open('/root/repo/gpurun_out/r02f_tile_fast.cuh').read().splitlines()
+src = open('/root/repo/gpurun_out/r02h_tile_fast.cuh').read().splitlines()
 def find(t): return [i + 1 for i, l in enumerate(src) if t in l][0]
 marks = [(find('static __device__ __forceinline__ float rcp_approx'), 'find_hsml_fast'),
          (find('template <int MODE>'), 'kernel setup / tile loop'),
