@@ -182,11 +182,20 @@ def test_power_of_two_box_and_ragged_tail():
         g.find_sph_quantities()
         g.find_sph_quantities()       # warm: the tile path
         res[name] = g.download()
+        # ... and the displacement: the last particle's pair partner in the packed phase 2 of the
+        # fast sweep is a pad slot (n is odd) and must contribute exactly nothing
+        g.wvt_iteration(0.0085)
+        g.wvt_iteration(0.0085)
+        moved = g.download()
+        assert np.isfinite(moved["pos"]).all() and np.isfinite(moved["hsml"]).all(), name
+        res[name + "_moved"] = moved
     os.environ.pop("TOYGPU_NO_TILES", None)
     for k in ("hsml", "rho", "varhsml"):
         assert np.array_equal(res["tile"][k], res["generic"][k]), k
         rel = _rel(res["fast"][k], res["generic"][k])
         assert (rel <= TOL).mean() >= FRAC_WITHIN and rel.max() <= MAX_REL, (k, rel.max())
+    assert np.array_equal(res["tile_moved"]["id"], res["generic_moved"]["id"])
+    assert np.array_equal(res["tile_moved"]["pos"], res["generic_moved"]["pos"])
 
 
 def test_full_size_merger_1e6_all_modes():

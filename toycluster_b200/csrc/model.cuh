@@ -159,8 +159,10 @@ k_reorder_model(int n, const int *__restrict__ idx, const float4 *__restrict__ p
         const size_t n8 = ((size_t)n + 7) & ~(size_t)7;
         const float qnan = __int_as_float(0x7fc00000);
         soa[k] = qnan; soa[n8 + k] = qnan; soa[2 * n8 + k] = qnan;
+        // the pair-interleaved copy gets a FINITE far-away pad: the partner of the last particle
+        // is evaluated by the packed phase 2 with weight 0, and 0 * NaN would poison its sums
         float *q = pwp + 8 * (size_t)(k >> 1) + (k & 1);
-        q[0] = qnan; q[2] = qnan; q[4] = qnan; q[6] = 0.f;
+        q[0] = 1e18f; q[2] = 1e18f; q[4] = 1e18f; q[6] = 0.f;
         pw[k] = make_float4(qnan, qnan, qnan, 0.f);          // pw has n8 entries: the pad is addressable
     }
     const double s = block_sum(cube, sm);

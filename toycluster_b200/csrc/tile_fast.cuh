@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 const bool live = k < nU;
                 const bool fl0 = df_flagged(w0), fl1 = df_flagged(w1);
                 r20 = (live && !fl0) ? r20 : 3.0e38f;       // dead: the pad, hits of the second pass;
-                r21 = (live && !fl1) ? r21 : 3.0e38f;       // (the NaN pad of an odd n compares false)
+                r21 = (live && !fl1) ? r21 : 3.0e38f;       // (the pad of an odd n is finite and far away)
                 sawflag |= live && (fl0 | fl1);
                 const bool inA0 = r20 < hA2, inB0 = r20 < hB2, inW0 = r20 < hsw2;
                 const bool inA1 = r21 < hA2, inB1 = r21 < hB2, inW1 = r21 < hsw2;

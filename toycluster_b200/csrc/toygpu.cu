@@ -32,6 +32,7 @@
 #include "sph.cuh"
 #include "tile.cuh"
 #include "tile_fast.cuh"
+#include "sph_fast.cuh"
 #include "bfield.cuh"
 #include "comm.cuh"
 #include <thread>
@@ -105,7 +106,7 @@ struct tg_ctx {
     double *gscratch = nullptr;
     int sweep_blocks = 0;
     int *tile_ng = nullptr, *tile_groups = nullptr, *worklist = nullptr;
-    int tile_blocks = 0, fast_blocks = 0;
+    int tile_blocks = 0, fast_blocks = 0, sweep_fast_blocks = 0;
     bool use_tiles = true;
 
     // AoS records of the driver, resident on the device (tg_upload / tg_download)
@@ -489,6 +490,20 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
                                                           TF_WARPS * 32, TF_SMEM));
         if (per < 1) per = 1;
         c->fast_blocks = prop.multiProcessorCount * per;
+    }
+    {
+        auto set = [&](const void *f) {
+            return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM);
+        };
+        CUC(set((const void *)k_sweep_fast<MODE_DENSITY, false>));
+        CUC(set((const void *)k_sweep_fast<MODE_DENSITY, true>));
+        CUC(set((const void *)k_sweep_fast<MODE_DENSITY | MODE_WVT, false>));
+        CUC(set((const void *)k_sweep_fast<MODE_DENSITY | MODE_WVT, true>));
+        int per = 1;
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_sweep_fast<MODE_DENSITY | MODE_WVT, false>,
+                                                          SF_WARPS * 32, SF_SMEM));
+        if (per < 1) per = 1;
+        c->sweep_fast_blocks = prop.multiProcessorCount * per;
     }
     CUC(dmalloc(&c->tile_ng, (size_t)t.lvl_n[0]));
     CUC(dmalloc(&c->tile_groups, (size_t)t.lvl_n[0] * TL_ENT));
@@ -981,6 +996,14 @@ template <int MODE> static int launch_generic(tg_ctx *c, SweepArgs a)
     const size_t smem = (size_t)SW_WARPS * SW_LCAP * sizeof(double);
     CU(cudaMemsetAsync(c->flags, 0, sizeof(int), c->stream));       // work counter
     a.next = c->flags;
+    constexpr bool has_fast = MODE == MODE_DENSITY || MODE == (MODE_DENSITY | MODE_WVT);
+    if constexpr (has_fast) {
+        if (c->cfg.flags & TG_FAST) {       // the cold pass of TG_FAST (sph_fast.cuh)
+            k_sweep_fast<MODE, false><<<c->sweep_fast_blocks, SF_WARPS * 32, SF_SMEM, c->stream>>>(a);
+            LAUNCH_CHECK();
+            return TG_OK;
+        }
+    }
     k_sweep<MODE, false><<<c->sweep_blocks, SW_WARPS * 32, smem, c->stream>>>(a);
     LAUNCH_CHECK();
     return TG_OK;
@@ -1012,6 +1035,14 @@ template <int MODE> static int launch_tiled(tg_ctx *c, SweepArgs a)
     }
     LAUNCH_CHECK();
     a.next = c->flags + 6;
+    constexpr bool has_fast_generic = MODE == MODE_DENSITY || MODE == (MODE_DENSITY | MODE_WVT);
+    if constexpr (has_fast_generic) {
+        if (fast) {                          // hand-backs of the fast tile sweep stay in FP32
+            k_sweep_fast<MODE, true><<<c->sweep_fast_blocks, SF_WARPS * 32, SF_SMEM, c->stream>>>(a);
+            LAUNCH_CHECK();
+            return TG_OK;
+        }
+    }
     k_sweep<MODE, true><<<c->sweep_blocks, SW_WARPS * 32, smem, c->stream>>>(a);
     LAUNCH_CHECK();
     return TG_OK;
