@@ -1,5 +1,5 @@
 set -x
-python scripts/sanitize_small.py > gpurun_out/san_plain.log 2>&1 && timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python scripts/sanitize_small.py > gpurun_out/san_memcheck.log 2>&1; echo "rc=$?" >> gpurun_out/san_memcheck.log; tail -6 gpurun_out/san_memcheck.log
-python scripts/handbacks.py merger_sub_1e7 > gpurun_out/handbacks_sub.log 2>&1; cat gpurun_out/handbacks_sub.log
-timeout 1500 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/b_ref.json 2> gpurun_out/b_ref.err; cat gpurun_out/b_ref.json; tail -3 gpurun_out/b_ref.err
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/b_final1.json 2> gpurun_out/b_final1.err; cat gpurun_out/b_final1.json
+python scripts/dbg_fast_pow2.py > gpurun_out/dbg_pow2.log 2>&1; cat gpurun_out/dbg_pow2.log
+timeout 1200 python -m pytest tests/test_gpu_fast.py -q -m gpu > gpurun_out/t_fast5.log 2>&1; echo "rc=$?" >> gpurun_out/t_fast5.log
+grep -E "FAILED|ERROR|passed|failed|rc=|^E  " gpurun_out/t_fast5.log | tail -12
+python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b_i.json 2> gpurun_out/b_i.err; cut -c1-400 gpurun_out/b_i.json

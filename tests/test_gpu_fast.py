@@ -194,8 +194,10 @@ def test_power_of_two_box_and_ragged_tail():
         assert np.array_equal(res["tile"][k], res["generic"][k]), k
         rel = _rel(res["fast"][k], res["generic"][k])
         assert (rel <= TOL).mean() >= FRAC_WITHIN and rel.max() <= MAX_REL, (k, rel.max())
+    # (the FP64 tree sums of the displacement associate differently on the two paths: last bit)
     assert np.array_equal(res["tile_moved"]["id"], res["generic_moved"]["id"])
-    assert np.array_equal(res["tile_moved"]["pos"], res["generic_moved"]["pos"])
+    for name in ("tile_moved", "fast_moved"):
+        assert np.abs(res[name]["pos"] - res["generic_moved"]["pos"]).max() <= 2 * np.spacing(np.float32(box)), name
 
 
 def test_full_size_merger_1e6_all_modes():

@@ -12,17 +12,18 @@
 #define SF_LCAP 2368                     // >= TG_NGBMAX, whole passes of 64
 #define SF_SMEM (SF_WARPS * SF_LCAP * 4)
 
-// tree.c:67-88 as a value: the float, FMA-free r^2 of the closest image (and the signed
-// closest-image separation for the displacement).
+// tree.c:67-88 as a value: the float, FMA-free r^2 of the closest image for the predicate, and
+// (r2a, signed separations) from wrap_sep for the value of r and the direction.
 static __device__ __forceinline__ float ngb_r2(float xi, float yi, float zi, float xj, float yj, float zj,
-                                               float box, float boxhalf, float &sdx, float &sdy, float &sdz)
+                                               float box, float boxhalf, float &r2a, float &sdx, float &sdy,
+                                               float &sdz)
 {
-    const float dx = __fsub_rn(xi, xj), dy = __fsub_rn(yi, yj), dz = __fsub_rn(zi, zj);
-    float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+    float ax = fabsf(__fsub_rn(xi, xj)), ay = fabsf(__fsub_rn(yi, yj)), az = fabsf(__fsub_rn(zi, zj));
     if (ax > boxhalf) ax = __fsub_rn(ax, box);
     if (ay > boxhalf) ay = __fsub_rn(ay, box);
     if (az > boxhalf) az = __fsub_rn(az, box);
-    sdx = copysignf(1.f, dx) * ax; sdy = copysignf(1.f, dy) * ay; sdz = copysignf(1.f, dz) * az;
+    sdx = wrap_sep(xi, xj, box, boxhalf); sdy = wrap_sep(yi, yj, box, boxhalf); sdz = wrap_sep(zi, zj, box, boxhalf);
+    r2a = fmaf(sdz, sdz, fmaf(sdy, sdy, sdx * sdx));
     return sq3_nofma(ax, ay, az);
 }
 
@@ -72,13 +73,13 @@ __global__ void __launch_bounds__(SF_WARPS * 32) k_sweep_fast(const SweepArgs a)
                         float r = 0;
                         if (k < a.t.n) {
                             const float4 p = a.pw[k];
-                            float sx_, sy_, sz_;
-                            const float r2 = ngb_r2(pi.x, pi.y, pi.z, p.x, p.y, p.z, box, boxhalf, sx_, sy_, sz_);
+                            float sx_, sy_, sz_, r2a;
+                            const float r2 = ngb_r2(pi.x, pi.y, pi.z, p.x, p.y, p.z, box, boxhalf, r2a, sx_, sy_, sz_);
                             hit = r2 < h2 && (!df_flagged(p.w) ||
                                               defect_open(a.dnodes + a.dmap[k], pi.x, pi.y, pi.z, h, box, boxhalf));
-                            const float y = rsqrt_approx(fmaxf(r2, 1e-35f));
-                            r = r2 * y;
-                            r = fmaf(0.5f * y, fmaf(-r, r, r2), r);
+                            const float y = rsqrt_approx(fmaxf(r2a, 1e-35f));
+                            r = r2a * y;
+                            r = fmaf(0.5f * y, fmaf(-r, r, r2a), r);
                         }
                         const unsigned m = __ballot_sync(FULL_MASK, hit);
                         const int slot = cnt + __popc(m & lt);
@@ -123,12 +124,13 @@ __global__ void __launch_bounds__(SF_WARPS * 32) k_sweep_fast(const SweepArgs a)
                     float f = 0, dX = 0, dY = 0, dZ = 0;
                     if (k < a.t.n) {
                         const float4 p = a.pw[k];
-                        const float r2 = ngb_r2(pi.x, pi.y, pi.z, p.x, p.y, p.z, box, boxhalf, dX, dY, dZ);
+                        float r2a;
+                        const float r2 = ngb_r2(pi.x, pi.y, pi.z, p.x, p.y, p.z, box, boxhalf, r2a, dX, dY, dZ);
                         hit = r2 < hs2 && (!df_flagged(p.w) ||
                                            defect_open(a.dnodes + a.dmap[k], pi.x, pi.y, pi.z, hs, box, boxhalf));
-                        const float y = rsqrt_approx(fmaxf(r2, 1e-35f));
-                        float r = r2 * y;
-                        r = fmaf(0.5f * y, fmaf(-r, r, r2), r);
+                        const float y = rsqrt_approx(fmaxf(r2a, 1e-35f));
+                        float r = r2a * y;
+                        r = fmaf(0.5f * y, fmaf(-r, r, r2a), r);
                         const float hp = (pi.w + fabsf(p.w)) * cn;
                         const float u = fminf(r * rcp_approx(hp), 1.f);
                         const float t = 1.f - u, t2 = t * t, t4 = t2 * t2;

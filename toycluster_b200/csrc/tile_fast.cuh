@@ -75,6 +75,20 @@ static __device__ __forceinline__ float rsqrt_approx(float x)
     return y;
 }
 
+// Closest-image separation xi - xj -+ Boxsize, accurate in float.  The reference's neighbour
+// predicate works on fl(xi - xj) -+ Boxsize (tree.c:67-78; reproduced for the predicate), but
+// Find_hsml and the displacement take the separation from FP64 differences (sph.c:111-126).  For
+// a pair across the periodic boundary fl(xi - xj) has already lost the low bits (error 2^-24 of
+// Boxsize, 1e-5 of a separation of Boxsize/300); going through xi - Boxsize (exact for xi >
+// Boxsize/2, Sterbenz) or xj - Boxsize keeps the float result within an ulp of the FP64 one.
+static __device__ __forceinline__ float wrap_sep(float xi, float xj, float box, float boxhalf)
+{
+    const float d = xi - xj;
+    if (d > boxhalf) return (xi - box) - xj;
+    if (d < -boxhalf) return xi - (xj - box);
+    return d;
+}
+
 // Sum of two doubles per lane over the warp with 6 shuffle steps instead of 10: the first
 // step trades one quantity for the other between lane pairs, the last one trades the totals.
 static __device__ __forceinline__ void warp_sum2(double &a, double &b)
@@ -389,6 +403,13 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     if (az > boxhalf) az = __fsub_rn(az, box);
                 }
                 float r2 = sq3_nofma(ax, ay, az);                                // tree.c:88
+                // the value of r (and the direction of the displacement): accurate separations
+                float ex = dx, ey = dy, ez = dz, r2a = r2;
+                if (!interior) {
+                    ex = wrap_sep(pi.x, pj.x, box, boxhalf); ey = wrap_sep(pi.y, pj.y, box, boxhalf);
+                    ez = wrap_sep(pi.z, pj.z, box, boxhalf);
+                    r2a = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                }
                 const bool flagged = df_flagged(pj.w);
                 // dead lanes: the pad of the last batch, and the hits the other pass takes
                 r2 = (k < nU && flagged == SLOW) ? r2 : 3.0e38f;
@@ -404,9 +425,9 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     if (inW) inW = defect_open(path, pi.x, pi.y, pi.z, hsw, box, boxhalf);
                 }
                 // r = sqrt(r2): MUFU.RSQ and one Newton step; the target itself (r2 = 0) gives 0
-                const float y = rsqrt_approx(fmaxf(r2, 1e-35f));
-                float r = r2 * y;
-                r = fmaf(0.5f * y, fmaf(-r, r, r2), r);
+                const float y = rsqrt_approx(fmaxf(r2a, 1e-35f));
+                float r = r2a * y;
+                r = fmaf(0.5f * y, fmaf(-r, r, r2a), r);
                 if (MODE & MODE_DENSITY) {
                     const unsigned mA = __ballot_sync(FULL_MASK, inA);
                     const unsigned mBo = __ballot_sync(FULL_MASK, inB) & ~mA;
@@ -423,9 +444,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     const float Q = fmaf(fmaf(16.f, u, 7.f), u, 1.f);
                     const bool use = inA && gidx != i;                           // sph.c:247 skips i itself
                     const float f = use ? (t4 * t3) * u * Q * (Afy * y) : 0.f;    // weight (dwk / r folded in)
-                    const float dX = __int_as_float(__float_as_int(ax) ^ (__float_as_int(dx) & 0x80000000));
-                    const float dY = __int_as_float(__float_as_int(ay) ^ (__float_as_int(dy) & 0x80000000));
-                    const float dZ = __int_as_float(__float_as_int(az) ^ (__float_as_int(dz) & 0x80000000));
+                    const float dX = ex, dY = ey, dZ = ez;
                     const float dAx = ax_i - a.apot[3 * (size_t)gidx], dAy = ay_i - a.apot[3 * (size_t)gidx + 1],
                                 dAz = az_i - a.apot[3 * (size_t)gidx + 2];
                     sx = fmaf(f, dZ * dAy - dY * dAz, sx);
@@ -442,10 +461,9 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     const float P = fmaf(fmaf(fmaf(32.f, u, 25.f), u, 8.f), u, 1.f);
                     const bool use = inW && gidx != i;                           // :141
                     const float f = use ? (t4 * t4) * P * (Afy * y) : 0.f;
-                    // signed closest-image separation: sign(d) * (|d| [- Boxsize])
-                    sx = fmaf(f, __int_as_float(__float_as_int(ax) ^ (__float_as_int(dx) & 0x80000000)), sx);
-                    sy = fmaf(f, __int_as_float(__float_as_int(ay) ^ (__float_as_int(dy) & 0x80000000)), sy);
-                    sz = fmaf(f, __int_as_float(__float_as_int(az) ^ (__float_as_int(dz) & 0x80000000)), sz);
+                    sx = fmaf(f, ex, sx);
+                    sy = fmaf(f, ey, sy);
+                    sz = fmaf(f, ez, sz);
                     if (use && u < 1.f) npair++;
                 }
             };
@@ -456,16 +474,26 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
             f32x2 sx2 = pack2(0.f, 0.f), sy2 = sx2, sz2 = sx2;
             auto batch2 = [&](const int k, const int pidx, const ulonglong2 A, const ulonglong2 B) {
                 f32x2 dx2 = sub2(xi2, A.x), dy2 = sub2(yi2, A.y), dz2 = sub2(zi2, B.x);
+                f32x2 ex2 = dx2, ey2 = dy2, ez2 = dz2;    // accurate separations (wrap_sep): r, direction
                 if (!interior) {
-                    // closest image: d - Boxsize * rint(d / Boxsize) -- one rounded subtraction, the
-                    // value of tree.c:70-78 up to its sign; rint can only differ from the reference's
-                    // compare for |d| within 1e-7 of Boxsize/2, which is no hit for either image
-                    // (the tile walk only admits R < 0.49 Boxsize)
+                    // closest image for the PREDICATE: d - Boxsize * rint(d / Boxsize) -- one rounded
+                    // subtraction, the value of tree.c:70-78 up to its sign; rint can only differ from
+                    // the reference's compare for |d| within 1e-7 of Boxsize/2, which is no hit for
+                    // either image (the tile walk only admits R < 0.49 Boxsize).
+                    // ... and for the VALUE: (xi - k+ Boxsize) - (xj + k- Boxsize) with k = rint(...) in
+                    // {-1, 0, 1}, k+ = (k k + k)/2, k- = (k - k k)/2: the intermediate is exact
                     const float ibox = 1.f / box;
                     const f32x2 ib2 = pack2(ibox, ibox), mg2 = pack2(12582912.f, 12582912.f), nb2 = pack2(-box, -box);
-                    dx2 = fma2(sub2(fma2(dx2, ib2, mg2), mg2), nb2, dx2);
-                    dy2 = fma2(sub2(fma2(dy2, ib2, mg2), mg2), nb2, dy2);
-                    dz2 = fma2(sub2(fma2(dz2, ib2, mg2), mg2), nb2, dz2);
+                    const f32x2 pb2 = pack2(box, box), half2 = pack2(0.5f, 0.5f);
+                    auto wrap2 = [&](f32x2 &d, f32x2 &e, const f32x2 xi, const f32x2 xj) {
+                        const f32x2 k = sub2(fma2(d, ib2, mg2), mg2);
+                        const f32x2 kk = mul2(k, k);
+                        e = sub2(fma2(mul2(add2(kk, k), half2), nb2, xi), fma2(mul2(sub2(k, kk), half2), pb2, xj));
+                        d = fma2(k, nb2, d);
+                    };
+                    wrap2(dx2, ex2, xi2, A.x);
+                    wrap2(dy2, ey2, yi2, A.y);
+                    wrap2(dz2, ez2, zi2, B.x);
                 }
                 // tree.c:88 without FMA: packed products, SCALAR sums (ptxas would contract a packed
                 // product feeding a packed add into one FFMA2)
@@ -483,8 +511,12 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 const bool inA0 = r20 < hA2, inB0 = r20 < hB2, inW0 = r20 < hsw2;
                 const bool inA1 = r21 < hA2, inB1 = r21 < hB2, inW1 = r21 < hsw2;
                 // r = sqrt(r2): MUFU.RSQ and one Newton step
-                const float y0 = rsqrt_approx(fmaxf(r20, 1e-35f)), y1 = rsqrt_approx(fmaxf(r21, 1e-35f));
-                const f32x2 y2 = pack2(y0, y1), r2v = pack2(r20, r21);
+                float a20 = r20, a21 = r21;               // r^2 for the VALUE of r
+                if (!interior) unpack2(fma2(ez2, ez2, fma2(ey2, ey2, mul2(ex2, ex2))), a20, a21);
+                const float y0 = rsqrt_approx(fmaxf(a20, 1e-35f)), y1 = rsqrt_approx(fmaxf(a21, 1e-35f));
+                f32x2 r2v = pack2(r20, r21);
+                if (!interior) r2v = fma2(ez2, ez2, fma2(ey2, ey2, mul2(ex2, ex2)));
+                const f32x2 y2 = pack2(y0, y1);
                 f32x2 rr = mul2(r2v, y2);
                 rr = fma2(mul2(y2, pack2(0.5f, 0.5f)), fma2(sub2(pack2(0.f, 0.f), rr), rr, r2v), rr);
                 float r0, r1;
@@ -516,9 +548,9 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     unpack2(mul2(mul2(mul2(t4, t4), P), mul2(pack2(Afy, Afy), y2)), f0, f1);
                     const bool use0 = inW0 && 2 * pidx != i, use1 = inW1 && 2 * pidx + 1 != i;   // :141
                     const f32x2 f2 = pack2(use0 ? f0 : 0.f, use1 ? f1 : 0.f);
-                    sx2 = fma2(f2, dx2, sx2);
-                    sy2 = fma2(f2, dy2, sy2);
-                    sz2 = fma2(f2, dz2, sz2);
+                    sx2 = fma2(f2, ex2, sx2);
+                    sy2 = fma2(f2, ey2, sy2);
+                    sz2 = fma2(f2, ez2, sz2);
                     if (use0 && fminf(u0, 1.f) < 1.f) npair++;
                     if (use1 && fminf(u1, 1.f) < 1.f) npair++;
                 }
