@@ -1,5 +1,5 @@
 set -x
-python scripts/dbg_fast_pow2.py > gpurun_out/dbg_pow2.log 2>&1; cat gpurun_out/dbg_pow2.log
-timeout 1200 python -m pytest tests/test_gpu_fast.py -q -m gpu > gpurun_out/t_fast5.log 2>&1; echo "rc=$?" >> gpurun_out/t_fast5.log
-grep -E "FAILED|ERROR|passed|failed|rc=|^E  " gpurun_out/t_fast5.log | tail -12
-python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b_i.json 2> gpurun_out/b_i.err; cut -c1-400 gpurun_out/b_i.json
+timeout 2400 python -m pytest tests -q -m gpu > gpurun_out/t_all7.log 2>&1; echo "rc=$?" >> gpurun_out/t_all7.log
+grep -E "FAILED|ERROR|passed|failed|rc=|^E  " gpurun_out/t_all7.log | tail -20
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/b_fast2.json 2> gpurun_out/b_fast2.err; cut -c1-330 gpurun_out/b_fast2.json; tail -2 gpurun_out/b_fast2.err
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/b_final1b.json 2> gpurun_out/b_final1b.err; cut -c1-330 gpurun_out/b_final1b.json

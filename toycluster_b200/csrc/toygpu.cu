@@ -123,6 +123,7 @@ struct tg_ctx {
     unsigned long long *halo_counts = nullptr;   // tg_halo_ids
     ncclComm_t comm = nullptr;
     double *errbuf = nullptr;       // [3 * nranks] gathered (err sum, err max, stop flag)
+    double *hpin = nullptr;         // page-locked host words for the per-step read-backs (truly async copies)
     std::vector<tg_ctx *> kids;
 
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -240,6 +241,7 @@ extern "C" int tg_destroy(tg_ctx *c)
     cudaSetDevice(c->cfg.device);
     if (c->comm) nccl_api()->CommDestroy(c->comm);
     if (c->errbuf) cudaFree(c->errbuf);
+    if (c->hpin) cudaFreeHost(c->hpin);
     if (c->halo_extra) cudaFree(c->halo_extra);
     if (c->n_limited) cudaFree(c->n_limited);
     if (c->ngb_scratch) cudaFree(c->ngb_scratch);
@@ -434,6 +436,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     c->npartial = cdiv(n, RED_THREADS);
     CUC(dmalloc(&c->partial, (size_t)2 * c->npartial));
     CUC(dmalloc(&c->scal, 4));
+    CUC(cudaHostAlloc((void **)&c->hpin, sizeof(double) * (2 * nranks + 8), cudaHostAllocDefault));
     CUC(dmalloc(&c->flags, 12));
     CUC(dmalloc(&c->counters, 12));
     CUC(cudaMemsetAsync(c->flags, 0, 12 * sizeof(int), c->stream));
@@ -1053,9 +1056,12 @@ static int check_flags(tg_ctx *c, bool swept = true)
         const int rc = reduce_flags_max(c, c->flags + 1, 2);
         if (rc) return rc;
     }
-    CU(cudaMemcpyAsync(f, c->flags, sizeof f, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(dc, c->defect.counts, sizeof dc, cudaMemcpyDeviceToHost, c->stream));
+    int *hp = (int *)(c->hpin + 2 * c->cfg.nranks);          // page-locked: 10 + 4 ints
+    CU(cudaMemcpyAsync(hp, c->flags, sizeof f, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hp + 10, c->defect.counts, sizeof dc, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    memcpy(f, hp, sizeof f);
+    memcpy(dc, hp + 10, sizeof dc);
     c->stats.displaced_nodes = dc[0];
     c->stats.displaced_particles = dc[3];
     c->stats.displaced_overflow = dc[2];
@@ -1218,8 +1224,8 @@ extern "C" int tg_wvt_begin(tg_ctx *c, double step_guess, double *err_sum, doubl
         LAUNCH_CHECK();
     }
     if (c->comm) NC(nccl_api()->AllGather(c->scal + 1, c->errbuf, 2, ncclFloat64, c->comm, c->stream));
-    std::vector<double> h(2 * R);
-    CU(cudaMemcpyAsync(h.data(), c->comm ? c->errbuf : c->scal + 1, sizeof(double) * 2 * R, cudaMemcpyDeviceToHost, c->stream));
+    double *h = c->hpin;                                     // page-locked: the copy really is asynchronous
+    CU(cudaMemcpyAsync(h, c->comm ? c->errbuf : c->scal + 1, sizeof(double) * 2 * R, cudaMemcpyDeviceToHost, c->stream));
     if ((rc = check_flags(c))) return rc;                    // synchronises
     double esum = 0, emax = 0;
     for (int r = 0; r < R; r++) { esum += h[2 * r]; emax = std::max(emax, h[2 * r + 1]); }
