@@ -38,3 +38,22 @@ exw, _ = run(0, 1, h0); faw, sw = run(tc.FAST, 1, h0); fag, sg = run(tc.FAST, 1,
 cmp(faw, exw, "warm from exact cold: fast(tile) ")
 cmp(fag, exw, "warm from exact cold: fast(gen)  ")
 print("handed back", sw["handed_back"], sw["handback_why"], "searches", sw["searches"], "iters", sw["hsml_iters"], "exact iters", _["hsml_iters"] if False else "")
+
+# ---- displacement: one WVT iteration from the same warm state, fast vs exact, path by path
+def wvt(flags, notiles=False):
+    if notiles: os.environ["TOYGPU_NO_TILES"] = "1"
+    else: os.environ.pop("TOYGPU_NO_TILES", None)
+    g = tc.HotPath(n, box, 1.0, 1e5, halo, flags=flags)
+    g.upload(pos, h0)
+    g.wvt_iteration(0.0085)
+    hw, dl = g.wvt_scratch(); o = g.download(); st = g.stats(); g.close()
+    return dl, o, st
+de, oe, se = wvt(0, True)
+for tag, fl, nt in (("exact tile", 0, False), ("fast tile ", tc.FAST, False), ("fast gen  ", tc.FAST, True)):
+    d, o, st = wvt(fl, nt)
+    sc = np.linalg.norm(de, axis=1)
+    err = np.linalg.norm(d.astype(np.float64) - de, axis=1) / np.maximum(sc, 1e-30)
+    print(tag, "delta rel err: median %.2e q99 %.2e q999 %.2e max %.2e | |delta|*box median %.3g max %.3g | handed back %d pairs %d vs %d" % (
+        np.median(err), np.quantile(err, .99), np.quantile(err, .999), err.max(), np.median(sc) * box, sc.max() * box, st["handed_back"], st["pair_evals"], se["pair_evals"]))
+    worst = np.argsort(err)[-3:]
+    print("   worst:", [(int(k), float(err[k]), de[k].tolist(), d[k].tolist()) for k in worst])
