@@ -121,10 +121,7 @@ static __device__ __forceinline__ float tile_radius(float hA, float hw_raw, floa
 #define TW_WARPS 8
 #define TW_QCAP 320                      // accepted nodes per level a tile may have (TL_ENT + slack)
 
-#ifndef TW_MINBLOCKS
-#define TW_MINBLOCKS 1
-#endif
-__global__ void __launch_bounds__(TW_WARPS * 32, TW_MINBLOCKS)
+__global__ void __launch_bounds__(TW_WARPS * 32)
 k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw, const float *__restrict__ hsml_in,
             const double *__restrict__ vsum, int tile_lo, int tile_hi, int *__restrict__ tile_ng,
             int *__restrict__ tile_groups, int rmode)

@@ -108,16 +108,9 @@ static __device__ __forceinline__ void warp_sum2(double &a, double &b)
 // u = r * inv with inv ~ 1/h from MUFU.RCP; its relative error e (exactly inv*h - 1, one FMA)
 // shifts every u alike, which is a first-order correction of the sum:
 //   Sw(u) = Sw(u (1+e)) - e * sum u w'(u) = Sw(u (1+e)) + 22 e Sv      (u w'(u) = -22 v(u)).
-// nA / hA (second-search lists only, else nA = cnt): the first nA entries are the ones within
-// hA, all others lie beyond it.  Two exact shortcuts follow: an iteration at hs < hA only has to
-// visit the first nA entries (the rest have u > 1 and contribute exactly 0), and the FIRST
-// iteration -- at 1.23 hA, where the list holds ~1.9 x 295 neighbours and the only question is
-// whether |wkNgb - 295| >= 147.5 (bisection, sph.c:186) -- can stop after the inner part as soon
-// as that part alone carries wkNgb past 443: every term is >= 0.
 static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const float *r, int cnt,
                                                       float &h_io, float &rho_out, float &drho_out,
-                                                      unsigned &evals, unsigned &iters,
-                                                      int nA = 1 << 30, float hA = 0.f)
+                                                      unsigned &evals, unsigned &iters)
 {
     const int lane = lane_id();
     const double mpart = a.bx.mpart;
@@ -154,23 +147,9 @@ static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const 
             sv2 = fma2(mul2(u, u), mul2(t7, Q), sv2);
         };
         // the caller padded the list to a multiple of 64 with entries far outside (u clamps to 1)
-        const int cnt64 = (cnt + 63) & ~63;
-        const int nin = min((nA + 63) & ~63, cnt64);       // whole passes that cover the inner part
-        const bool inner_only = hs < 0.9999 * (double)hA;   // everything beyond hA contributes 0
 #pragma unroll 2
-        for (int k = lane; k < nin; k += 64) pair(r[k], r[k + 32]);
+        for (int k = lane; k < cnt; k += 64) pair(r[k], r[k + 32]);
         float w0, w1, v0, v1;
-        bool certain_bisection = false;
-        if (it == 1 && nin < cnt64) {
-            // lower bound of wkNgb from the inner part (the correction terms are ~1e-7 of it)
-            unpack2(sw2, w0, w1);
-            const double lb = K_FOURPITHIRD * TF_KW * warp_sum((double)w0 + (double)w1);
-            certain_bisection = lb > 1.5 * TG_DESNNGB + 1.0;
-        }
-        if (!inner_only && !certain_bisection) {
-#pragma unroll 2
-            for (int k = nin + lane; k < cnt64; k += 64) pair(r[k], r[k + 32]);
-        }
         unpack2(sw2, w0, w1);
         unpack2(sv2, v0, v1);
         Sw = (double)w0 + (double)w1;
@@ -656,8 +635,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     if (cnt + lane < cnt64) rl[cnt + lane] = 3.0e38f;
                     if (cnt + 32 + lane < cnt64) rl[cnt + 32 + lane] = 3.0e38f;
                     __syncwarp();
-                    ok = cnt == cntA ? find_hsml_fast(a, rl, cnt, h, rho, drho, n_evals, n_iters)
-                                     : find_hsml_fast(a, rl, cnt, h, rho, drho, n_evals, n_iters, cntA, hA);
+                    ok = find_hsml_fast(a, rl, cnt, h, rho, drho, n_evals, n_iters);
                     why = 4;                                 // no convergence on the frozen list
                 }
                 if (!ok) { hand_back(i, why); continue; }
