@@ -224,6 +224,17 @@ int tg_halo_ids(tg_ctx *ctx, const tg_bfield *par, int32_t *ids, long long *npar
 /* Apot of the current order, apot[n][3] (what tg_make_magnetic_field or tg_set_apot left). */
 int tg_get_apot(tg_ctx *ctx, float *apot);
 
+/* Gadget block writer (io.c:85-133 add_block / fill_write_buffer): the gas part of
+ * a block's write buffer straight from the device's SoA arrays -- no AoS round trip and no
+ * per-particle host loop.  tg_set_output_order: order[k] = index IN THE CURRENT DEVICE ORDER of
+ * the particle the file holds at position k (what sort_particles(), positions.c:405-443, makes
+ * of the records after the path; NULL = the device order itself).  tg_fill_block writes
+ * n_gas * {3, 1, 1, 3, 1} floats of TG_BLOCK_{POS, RHO, HSML, BFLD, RHOMODEL} to `out`
+ * (io.c:141-166: P.Pos, SphP.Rho, SphP.Hsml, SphP.Bfld, SphP.Rho_Model as float). */
+enum { TG_BLOCK_POS = 0, TG_BLOCK_RHO = 1, TG_BLOCK_HSML = 2, TG_BLOCK_BFLD = 3, TG_BLOCK_RHOMODEL = 4 };
+int tg_set_output_order(tg_ctx *ctx, const size_t *order /* [n_gas] or NULL */);
+int tg_fill_block(tg_ctx *ctx, int block, float *out);
+
 /* ---- test hooks (parity with peano.c / sort.c / tree.c) ----------------------------- */
 /* Peano_Key of every uploaded particle, upload order (peano.c:63-71). */
 int tg_peano_keys(tg_ctx *ctx, uint64_t *hi, uint64_t *lo);

@@ -197,3 +197,33 @@ def test_reassign_on_the_device_writes_the_same_gadget_file(tmp_path):
     for label in c:
         if label != "BFLD":
             assert c[label] == g[label], label
+
+
+@pytest.mark.gpu
+def test_blocks_from_the_device_write_the_same_gadget_file(tmp_path):
+    """add_block() (io.c:85-133) from the shim -- the gas range of POS and the blocks
+    RHO, HSML, BFLD, RHOM are filled on the device from the SoA arrays in the file order
+    Reassign_particles_to_halos() left (tg_set_output_order / tg_fill_block); everything else of
+    the writer is io.c's own.  Two halos, so the file order differs from the device's."""
+    gpu_w = GPU + "_w"
+    if not (os.path.exists(CPU) and os.path.exists(gpu_w)):
+        pytest.skip("oracle/_ref/Toycluster_gpu_w not built (make -C oracle driver)")
+    for tag in ("c", "g"):
+        (tmp_path / f"{tag}.par").write_text(PAR.format(out=f"IC_{tag}", ntotal=30000, mass_ratio=0.3125, bnorm="60e-6"))
+    out_c = run(CPU, "c.par", tmp_path, {})
+    # TOYSHIM_POISON_RECORDS: the shim overwrites SphP.Rho/Hsml/Bfld/Rho_Model and the gas P.Pos of
+    # the driver's records with NaN just before the writer runs, so a block that were still
+    # filled from the records could not pass
+    out_g = run(gpu_w, "g.par", tmp_path, {"TOYGPU_FLAGS": "1", "TOYSHIM_POISON_RECORDS": "1"})
+    blk_c = [l for l in out_c.splitlines() if l.startswith("   Block ")]
+    blk_g = [l for l in out_g.splitlines() if l.startswith("   Block ")]
+    assert len(blk_c) == 8 and blk_c == blk_g
+    c, g = read_gadget2(tmp_path / "IC_c"), read_gadget2(tmp_path / "IC_g")
+    assert list(c) == list(g)
+    for label in c:
+        if label != "BFLD":
+            assert c[label] == g[label], label
+    bc = np.frombuffer(c["BFLD"], np.float32).reshape(-1, 3)
+    bg = np.frombuffer(g["BFLD"], np.float32).reshape(-1, 3)
+    scale = np.abs(bc).max(axis=1, keepdims=True) + 1e-30
+    assert (np.abs(bg - bc) / scale).max() < 1e-5

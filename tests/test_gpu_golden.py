@@ -287,3 +287,31 @@ def test_records_device_path_is_idempotent_and_pinned():
         g.close()
         res.append(first)
     assert res[0] == res[1]
+
+
+def test_gadget_blocks_from_the_soa_state():
+    """tg_set_output_order / tg_fill_block (io.c:85-133): a block's write buffer is
+    the field of particle order[k] at position k -- identity, a random file order, a bad index."""
+    w = workloads.make("merger_1e6", n_gas=20_001)
+    n = w.n_gas
+    g = tc.HotPath.from_workload(w)
+    g.upload(w.pos)
+    g.find_sph_quantities()
+    g.set_apot(np.repeat(np.linspace(0.1, 1, n, dtype=np.float32)[:, None], 3, 1) * [1, 0.5, 0.25])
+    g.bfld_from_rotA_sph()
+    o = g.download(bfld=True)
+    names = dict(POS="pos", RHO="rho", HSML="hsml", BFLD="bfld", RHOM="rho_model")
+    for label, key in names.items():
+        assert np.array_equal(g.fill_block(label), o[key]), label
+    order = np.random.default_rng(5).permutation(n)
+    g.set_output_order(order)
+    for label, key in names.items():
+        assert np.array_equal(g.fill_block(label), o[key][order]), label
+    g.set_output_order(None)
+    assert np.array_equal(g.fill_block("RHO"), o["rho"])
+    bad = order.copy()
+    bad[7] = n
+    with pytest.raises(tc.ToyGpuError):
+        g.set_output_order(bad)
+    # the failed call did not disturb the state: the sorted keys are still the records' keys
+    assert np.array_equal(g.download()["rho"], o["rho"])

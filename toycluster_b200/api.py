@@ -86,6 +86,7 @@ EXPORTS = [
     "tg_sort", "tg_find_ngb", "tg_guess_hsml", "tg_get_exchange",
     "tg_make_magnetic_field", "tg_get_apot", "tg_pin_host", "tg_unpin_host",
     "tg_comm_id", "tg_comm_init", "tg_halo_ids", "tg_sync_results",
+    "tg_set_output_order", "tg_fill_block",
 ]
 
 _lib = None
@@ -148,6 +149,8 @@ def load():
     lib.tg_pin_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.tg_unpin_host.argtypes = [C.c_void_p, C.c_void_p]
     lib.tg_halo_ids.argtypes = [C.c_void_p, C.POINTER(_BField), C.c_void_p, C.c_void_p]
+    lib.tg_set_output_order.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tg_fill_block.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.tg_comm_id.argtypes = [C.c_void_p]
     lib.tg_comm_init.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib
@@ -331,6 +334,23 @@ class HotPath:
         cnt = np.zeros(nh, np.int64)
         self._check(self.lib.tg_halo_ids(self._ctx, C.byref(par), _ptr(ids), _ptr(cnt)))
         return ids, cnt
+
+    BLOCKS = {"POS": (0, 3), "RHO": (1, 1), "HSML": (2, 1), "BFLD": (3, 3), "RHOM": (4, 1)}
+
+    def set_output_order(self, order=None):
+        """io.c:85-133 / positions.c:405-443: order[k] = current device index of the particle
+        the file holds at position k (None: the device order)."""
+        if order is not None:
+            order = np.ascontiguousarray(order, np.uint64)
+            assert order.shape == (self.n,)
+        self._check(self.lib.tg_set_output_order(self._ctx, _ptr(order)))
+
+    def fill_block(self, label):
+        """The gas part of the write buffer of one Gadget block, from the device arrays."""
+        code, vals = self.BLOCKS[label]
+        out = np.empty((self.n, vals) if vals > 1 else self.n, np.float32)
+        self._check(self.lib.tg_fill_block(self._ctx, code, _ptr(out)))
+        return out
 
     def get_apot(self):
         out = np.empty((self.n, 3), np.float32)

@@ -121,6 +121,8 @@ struct tg_ctx {
     int *n_limited = nullptr;
     int *ngb_scratch = nullptr;        // tg_find_ngb
     unsigned long long *halo_counts = nullptr;   // tg_halo_ids
+    int *out_order = nullptr;       // tg_set_output_order: file position -> current device index
+    bool have_out_order = false;
     ncclComm_t comm = nullptr;
     double *errbuf = nullptr;       // [3 * nranks] gathered (err sum, err max, stop flag)
     double *hpin = nullptr;         // page-locked host words for the per-step read-backs (truly async copies)
@@ -246,6 +248,7 @@ extern "C" int tg_destroy(tg_ctx *c)
     if (c->n_limited) cudaFree(c->n_limited);
     if (c->ngb_scratch) cudaFree(c->ngb_scratch);
     if (c->halo_counts) cudaFree(c->halo_counts);
+    if (c->out_order) cudaFree(c->out_order);
     void *ptrs[] = {c->posh, c->id, c->apot, c->stage, c->key_hi, c->key_lo, c->key_tmp, c->idx, c->idx_tmp,
                     c->hist, c->pw, c->pwp, c->soa, c->hsml_in, c->rho_model, c->rm_state, c->rm_state_s, c->id_s, c->key_lo_s, c->apot_s,
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->sub_mem, c->cpl,
@@ -1512,6 +1515,83 @@ extern "C" int tg_get_stats(tg_ctx *c, tg_stats *out)
         return TG_OK;
     }
     *out = c->stats;
+    return TG_OK;
+}
+
+// ------------------------------------------------------------------ Gadget blocks
+
+// io.c:141-166 for the gas range: element k of the block's write buffer is the field of the
+// particle order[k] (the file order sort_particles() left, positions.c:405-443), read from the
+// SoA state.  One thread per output float; reads are gathers, writes are coalesced.
+__global__ void k_fill_block(int n, int block, const int *__restrict__ order, const float4 *__restrict__ posh,
+                             const float *__restrict__ rho, const float *__restrict__ bfld,
+                             const float *__restrict__ rm, float *__restrict__ out)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vals = (block == TG_BLOCK_POS || block == TG_BLOCK_BFLD) ? 3 : 1;
+    if (t >= (size_t)n * vals) return;
+    const int k = (int)(t / vals), comp = (int)(t - (size_t)k * vals);
+    const int src = order ? order[k] : k;
+    float v;
+    switch (block) {
+    case TG_BLOCK_POS: { const float4 p = posh[src]; v = comp == 0 ? p.x : (comp == 1 ? p.y : p.z); break; }
+    case TG_BLOCK_RHO: v = rho[src]; break;
+    case TG_BLOCK_HSML: v = posh[src].w; break;
+    case TG_BLOCK_BFLD: v = bfld[3 * (size_t)src + comp]; break;
+    default: v = rm[src]; break;
+    }
+    out[t] = v;
+}
+
+__global__ void k_order_from_host(int n, const unsigned long long *__restrict__ in, int *__restrict__ out, int *bad)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned long long v = in[k];
+    if (v >= (unsigned long long)n) { *bad = 1; out[k] = 0; return; }
+    out[k] = (int)v;
+}
+
+extern "C" int tg_set_output_order(tg_ctx *c, const size_t *order)
+{
+    if (!c) return TG_EINVAL;
+    TG_GROUP0(c, tg_set_output_order(k, order));          // the state is replicated on every rank
+    if (!order) { c->have_out_order = false; return TG_OK; }
+    CU(cudaSetDevice(c->cfg.device));
+    const int n = c->n;
+    if (!c->out_order) CU(dmalloc(&c->out_order, (size_t)n));
+    // size_t[n] crosses the bus as it is (through the unsorted-key scratch, dead once the index is built: 8 B per particle) and is
+    // narrowed and range-checked on the device
+    static_assert(sizeof(size_t) == 8, "size_t");
+    unsigned long long *tmp = (unsigned long long *)c->key_lo;
+    CU(cudaMemcpyAsync(tmp, order, sizeof(size_t) * n, cudaMemcpyHostToDevice, c->stream));
+    int *bad_dev = c->flags + 8;                           // scratch word of the tie fix-up
+    CU(cudaMemsetAsync(bad_dev, 0, sizeof(int), c->stream));
+    k_order_from_host<<<cdiv(n, 256), 256, 0, c->stream>>>(n, tmp, c->out_order, bad_dev);
+    LAUNCH_CHECK();
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (bad) return fail(c, TG_EINVAL, "tg_set_output_order: an index is outside [0, n_gas)");
+    c->have_out_order = true;
+    return TG_OK;
+}
+
+extern "C" int tg_fill_block(tg_ctx *c, int block, float *out)
+{
+    if (!c || !out || block < TG_BLOCK_POS || block > TG_BLOCK_RHOMODEL)
+        return fail(c, TG_EINVAL, "tg_fill_block: bad arguments");
+    TG_GROUP0(c, tg_fill_block(k, block, out));
+    if (c->poisoned) return fail(c, TG_EINVAL, "tg_fill_block: the last step failed; upload again");
+    CU(cudaSetDevice(c->cfg.device));
+    const int n = c->n;
+    const int vals = (block == TG_BLOCK_POS || block == TG_BLOCK_BFLD) ? 3 : 1;
+    const size_t total = (size_t)n * vals;
+    k_fill_block<<<cdiv((long long)total, 256), 256, 0, c->stream>>>(n, block, c->have_out_order ? c->out_order : nullptr,
+                                                                    c->posh, c->rho, c->bfld, c->rm_state, c->stage);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(out, c->stage, sizeof(float) * total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return TG_OK;
 }
 

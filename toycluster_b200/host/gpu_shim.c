@@ -234,6 +234,10 @@ void Reassign_particles_to_halos()
     /* sort_particles(), positions.c:405-443 */
     size_t *idx = Malloc((size_t)n * sizeof *idx);
     Qsort_Index(Omp.NThreads, idx, haloID, n, sizeof *haloID, &compare_int);
+#ifdef TOYGPU_SHIM_IO
+    /* the file order: record idx[k] of the device's order goes to position k */
+    check(tg_set_output_order(Ctx, idx), "tg_set_output_order");
+#endif
     for (size_t i = 0; i < (size_t)n; i++) {
         if (idx[i] == i)
             continue;
@@ -283,6 +287,74 @@ void Reassign_particles_to_halos()
     printf("   Subhalos %8d   %8d   %8d \n", Sub.Ntotal, Sub.Npart[0], Sub.Npart[1]);
 #endif
     Free(npart); Free(rs_gas); Free(stripped);
+}
+#endif
+
+#ifdef TOYGPU_SHIM_IO
+#if !defined(TOYGPU_SHIM_MAGNETIC_FIELD) || !defined(TOYGPU_SHIM_REASSIGN)
+#error "TOYGPU_SHIM_IO needs the device to hold the final Bfld and the file order: build with -DTOYGPU_SHIM_MAGNETIC_FIELD -DTOYGPU_SHIM_REASSIGN"
+#endif
+/* io.c:85-133.  With this defined the shim also replaces add_block(): the write
+ * buffers of the blocks the path owns -- the gas range of POS, and RHO, HSML, BFLD, RHOM -- come
+ * straight from the device's SoA arrays in the file order Reassign_particles_to_halos() left
+ * (tg_set_output_order above), without the per-particle fill_write_buffer() loop over the AoS
+ * records.  Nothing after the path changes those fields (Make_temperatures writes U,
+ * Make_velocities / Apply_kinematics write Vel).  The other particle types of POS and the
+ * blocks VEL, ID, U are filled from the driver's records as before; header, block framing and
+ * everything else are io.c's own (Write_output, write_header, set_block_info, my_fwrite).
+ * io.o is linked with its add_block weakened (objcopy -W, see oracle/Makefile). */
+#include "io.h"
+
+void add_block(FILE *fp, enum iofields iblock)
+{
+    set_block_info(iblock);
+
+    printf("   Block %d (%s)\n", iblock, Block.Name);
+
+    const size_t vals = Block.Val_per_element;
+    const size_t nData = Block.Ntot * vals * Block.Bytes_per_element;
+    void *write_buffer = Malloc(nData);
+
+    int dev = -1;
+    switch (iblock) {
+    case IO_POS: dev = TG_BLOCK_POS; break;
+    case IO_RHO: dev = TG_BLOCK_RHO; break;
+    case IO_HSML: dev = TG_BLOCK_HSML; break;
+    case IO_BFLD: dev = TG_BLOCK_BFLD; break;
+    case IO_RHOMODEL: dev = TG_BLOCK_RHOMODEL; break;
+    default: break;
+    }
+
+    /* tests: prove that the device blocks do not read the driver's records */
+    if (iblock == IO_POS && getenv("TOYSHIM_POISON_RECORDS"))
+        for (int i = 0; i < Param.Npart[0]; i++) {
+            P[i].Pos[0] = P[i].Pos[1] = P[i].Pos[2] = NAN;
+            SphP[i].Rho = SphP[i].Hsml = SphP[i].Rho_Model = NAN;
+            SphP[i].Bfld[0] = SphP[i].Bfld[1] = SphP[i].Bfld[2] = NAN;
+        }
+
+    size_t first = 0;                        /* first particle that comes from the records */
+    if (dev >= 0 && Ctx != NULL && Block.Npart[0] > 0) {
+        check(tg_fill_block(Ctx, dev, write_buffer), "tg_fill_block");
+        first = Block.Npart[0];
+    }
+    /* io.c:100-114: the six type ranges are consecutive */
+    for (size_t ipart = first, ibuf = first * vals; ipart < (size_t)Block.Ntot; ipart++, ibuf += vals)
+        fill_write_buffer(iblock, write_buffer, ipart, ibuf);
+
+    int blocksize = sizeof(int) + 4 * sizeof(char);          /* F90 records, io.c:116-129 */
+    my_fwrite(&blocksize, sizeof(int), 1, fp);
+    my_fwrite(&Block.Label, sizeof(char), 4, fp);
+    int nextblock = nData + 2 * sizeof(int);
+    my_fwrite(&nextblock, sizeof(int), 1, fp);
+    my_fwrite(&blocksize, sizeof(int), 1, fp);
+
+    blocksize = nData;
+    my_fwrite(&blocksize, sizeof(int), 1, fp);
+    my_fwrite(write_buffer, blocksize, 1, fp);
+    my_fwrite(&blocksize, sizeof(int), 1, fp);
+
+    free(write_buffer);
 }
 #endif
 
