@@ -281,7 +281,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     acc = dict(pair_evals=0, gathered=0, kernels=0, sweep_ms=0.0, step_ms=0.0, searches=0, hsml_iters=0,
-               handed_back=0)
+               handed_back=0, index_ms=0.0, tail_ms=0.0)
     t_wall = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
@@ -300,7 +300,8 @@ def main():
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    per_rank = torch.tensor([acc["sweep_ms"] / args.steps, acc["step_ms"] / args.steps],
+    per_rank = torch.tensor([acc["sweep_ms"] / args.steps, acc["step_ms"] / args.steps,
+                             acc["index_ms"] / args.steps, acc["tail_ms"] / args.steps],
                             dtype=torch.float64, device="cuda")
     if world > 1:
         allr = [torch.empty_like(per_rank) for _ in range(world)]
@@ -403,9 +404,11 @@ def main():
             "hsml_iters_per_particle": hsml_iters / args.steps / n,
             "handed_back_per_step": handed / args.steps,
             "gpu_launches": int(acc["kernels"]), "clocks": clocks, "roofline": roofline}
-    if world > 1:     # per-rank device times: load balance of the target partition
-        line["per_rank_ms"] = {"sweep": [round(v, 3) for v in per_rank[:, 0].tolist()],
-                               "step": [round(v, 3) for v in per_rank[:, 1].tolist()]}
+    # per-rank device times: load balance of the target partition (sweep), the part of a step every
+    # rank repeats for all n (index: keys, sort, model pass, box hierarchy, displaced nodes) and
+    # what follows the sweep (tail: error sums, move, exchange of the moved slices)
+    line["per_rank_ms"] = {k: [round(v, 3) for v in per_rank[:, j].tolist()]
+                           for j, k in enumerate(("sweep", "step", "index", "tail"))}
     if e2e:
         line["e2e"] = e2e
     if full:

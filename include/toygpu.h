@@ -123,6 +123,9 @@ typedef struct {
                                                 displaced-node candidate in reach, a third
                                                 search or density list full, no convergence on
                                                 the frozen list */
+    double index_ms;                 /* device time of keys + sort + index + model pass: the part of
+                                        a step every rank repeats for all n */
+    double tail_ms;                  /* device time after the sweep: error sums, move, exchange */
 } tg_stats;
 
 /* ---- life cycle -------------------------------------------------------------------- */

@@ -1,3 +1,2 @@
-set -x
-timeout 900 python -m pytest tests -q -m gpu -k "blocks" > gpurun_out/t_blocks.log 2>&1; echo "rc=$?" >> gpurun_out/t_blocks.log
-grep -E "FAILED|ERROR|passed|failed|rc=|^E  " gpurun_out/t_blocks.log | tail -20
+timeout 600 python scripts/time_variants.py > gpurun_out/variants7.log 2>&1; cat gpurun_out/variants7.log | cut -c1-100
+timeout 900 python -m pytest tests/test_gpu_fast.py -x -q -m gpu > gpurun_out/t_fast_p3.log 2>&1; tail -3 gpurun_out/t_fast_p3.log

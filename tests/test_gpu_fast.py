@@ -280,3 +280,49 @@ def test_fast_rot_a_on_the_tile_path():
     assert err.max() <= 1e-5, err.max()
     rel = np.linalg.norm(got.astype(np.float64) - want, axis=1) / np.maximum(np.linalg.norm(want, axis=1), 1e-30)
     assert np.quantile(rel, 0.99) <= 1e-4, np.quantile(rel, 0.99)
+
+
+def test_fast_tile_path_honours_displaced_nodes():
+    """The packed phase 2 of the fast tile sweep gathers from the pair-interleaved copy of the
+    positions; the displaced-node flag (defect.cuh: candidates the reference octree prunes,
+    tree.c:56-58,298-310) has to be set there too.  On an input where many nodes are displaced,
+    TG_FAST must follow the exact default mode -- which is bit-identical to the reference here
+    (test_displaced_nodes.py) -- on the targets whose neighbour sets the pruning changes, not the
+    brute-force sets of TG_EXACT_NEIGHBOURS.  No reference run needed: all three are the GPU's."""
+    w = workloads.make("merger_1e6", n_gas=150_000, seed=4)
+    n = w.n_gas
+    g = tc.HotPath.from_workload(w)
+    g.upload(w.pos)
+    g.wvt_iteration(0.0085)                         # cold start: a warm state to begin from
+    s = g.download()
+    g.close()
+    pos = workloads.snap_to_cell_planes(s["pos"], w.boxsize, 4000, levels=(4, 5, 6, 7, 8))
+
+    def one(flags):
+        h = tc.HotPath.from_workload(w, flags=flags)
+        h.upload(pos, s["hsml"])
+        h.wvt_iteration(0.0085)
+        o, st = h.download(), h.stats()
+        _, o["delta"] = h.wvt_scratch()
+        h.close()
+        return o, st
+
+    d, st_d = one(0)
+    e, _ = one(tc.EXACT_NEIGHBOURS)
+    f, st_f = one(tc.FAST)
+    assert st_d["displaced_nodes"] > 100 and st_f["displaced_particles"] == st_d["displaced_particles"]
+    assert st_f["handed_back"] < 0.2 * n, st_f       # the tile path did the work
+    assert np.array_equal(d["id"], e["id"]) and np.array_equal(d["id"], f["id"])
+    affected = d["hsml"] != e["hsml"]                # pruning changed the neighbour set
+    assert affected.sum() > 200, affected.sum()
+    rel_fd = _rel(f["hsml"], d["hsml"])
+    rel_fe = _rel(f["hsml"], e["hsml"])
+    assert (rel_fd <= TOL).mean() >= FRAC_WITHIN and rel_fd.max() <= MAX_REL, rel_fd.max()
+    big = affected & (_rel(e["hsml"], d["hsml"]) > 1e-4)       # ... by more than float noise
+    assert big.sum() > 50, big.sum()
+    assert (rel_fd[big] <= TOL).mean() >= 0.98, (rel_fd[big] <= TOL).mean()
+    assert (rel_fd[big] < rel_fe[big]).all()
+    # and the displacement of the affected targets follows the pruned sets as well
+    scale = np.maximum(np.linalg.norm(d["delta"], axis=1), 1e-30)
+    err = np.linalg.norm(f["delta"].astype(np.float64) - d["delta"], axis=1) / scale
+    assert np.quantile(err[affected], 0.9) <= 1e-4, np.quantile(err[affected], 0.9)

@@ -253,6 +253,31 @@ def test_sort_with_long_runs_of_nearly_equal_keys():
     assert np.array_equal(g.download()["pos"], pos[want])
 
 
+def test_sort_with_thousands_of_particles_in_one_sort_cell():
+    """Runs longer than the serial fix-up's cap (RS_TIE_CAP = 256): 3000 particles inside one
+    2^-16 Boxsize cell -- distinct floats, plus 700 exact duplicates of one of them -- are ordered
+    by a whole block (k_fix_long_ties) like every other run: full 128-bit key, then index."""
+    from oracle import port
+    w = workloads.make("merger_1e6", n_gas=6000)
+    rng = np.random.default_rng(12)
+    box = np.float32(w.boxsize)
+    cell = w.boxsize / 65536.0
+    corner = np.array([40000, 50001, 33333], np.float64) * cell
+    clump = (corner + rng.uniform(0.02, 0.98, (3000, 3)) * cell).astype(np.float32)
+    dup = np.repeat(clump[17:18], 700, axis=0)
+    pos = np.concatenate([w.pos[:6000], clump, dup]).astype(np.float32)
+    pos = pos[rng.permutation(len(pos))]
+    n = len(pos)
+    assert len(np.unique(clump, axis=0)) > 2500          # the cell really holds distinct positions
+    g = tc.HotPath(n, w.boxsize, w.mpart_gas, w.mtotal, w.halo_table())
+    g.upload(pos)
+    perm = g.sort()
+    want, hi, lo, ndup = port.sort(pos, w.boxsize)
+    assert ndup >= 700
+    assert np.array_equal(perm, want)
+    assert np.array_equal(g.download()["pos"], pos[want])
+
+
 def test_records_device_path_is_idempotent_and_pinned():
     """tg_upload / tg_download keep the driver's records resident on the device: a second
     download without an upload in between returns the same bytes (the records on the device are

@@ -63,7 +63,8 @@ class Stats(C.Structure):
                 ("kernels", C.c_ulonglong), ("sweep_ms", C.c_double), ("step_ms", C.c_double),
                 ("handed_back", C.c_ulonglong), ("displaced_nodes", C.c_ulonglong),
                 ("displaced_particles", C.c_ulonglong), ("displaced_overflow", C.c_ulonglong),
-                ("handback_why", C.c_ulonglong * 5)]
+                ("handback_why", C.c_ulonglong * 5),
+                ("index_ms", C.c_double), ("tail_ms", C.c_double)]
 
     def as_dict(self):
         return {k: (list(getattr(self, k)) if k == "handback_why" else getattr(self, k))

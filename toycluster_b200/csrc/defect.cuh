@@ -50,6 +50,7 @@ struct DefectTab {
                          // [4] big cells
     float4 *nodes;       // (centre, size) per path level, terminated by size == 0
     int *dmap;           // [n] path offset of a flagged particle
+    float *pwp;          // the pair-interleaved copy of pw (tile_fast.cuh): flagged there as well
     int cap_events, cap_nodes;
 };
 
@@ -66,6 +67,10 @@ static __device__ __forceinline__ float df_child(float parent, bool upper, float
 __global__ void k_defect_detect(int n, const float4 *__restrict__ pw, double box,
                                 const signed char *__restrict__ cpl, DefectTab d)
 {
+    // the node sizes of tree.c:304, one FP64 divide per level and block instead of per particle
+    __shared__ float s_size[DF_MAX_LEVEL + 2];
+    if (threadIdx.x <= DF_MAX_LEVEL) s_size[threadIdx.x] = df_size(box, threadIdx.x);
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c0 = cpl[i], c1 = i + 1 < n ? (int)cpl[i + 1] : -1;
@@ -95,7 +100,7 @@ __global__ void k_defect_detect(int n, const float4 *__restrict__ pw, double box
             if (e < d.cap_events) d.events[e] = make_int2(i, q);
             return;                               // deeper nodes of i lie underneath this one
         }
-        const float s = df_size(box, q);
+        const float s = s_size[q];
         cx = df_child(cx, bx, s);
         cy = df_child(cy, by, s);
         cz = df_child(cz, bz, s);
@@ -157,6 +162,12 @@ static __device__ void df_emit_path(int k, int n, float4 *__restrict__ pw, doubl
     d.dmap[k] = off;
     float *w = &pw[k].w;
     *w = __int_as_float(__float_as_int(*w) | 0x80000000);
+#ifndef TF_NO_PWP_FLAG
+    // ... and in the copy the packed phase 2 of the fast tile sweep gathers from: pair k / 2 is
+    // {x0, x1, y0, y1}, {z0, z1, w0, w1}
+    float *w2 = d.pwp + 8 * (size_t)(k >> 1) + (k & 1) + 6;
+    *w2 = __int_as_float(__float_as_int(*w2) | 0x80000000);
+#endif
     atomicAdd(&d.counts[3], 1);
 }
 

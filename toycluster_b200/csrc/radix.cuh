@@ -209,11 +209,14 @@ k_radix_scatter(int n, const uint64_t *__restrict__ keys_in, const int *__restri
 // handful of particles at most (the sorted bits resolve cells of 2^-16 Boxsize or finer), so a
 // serial insertion sort is fine.  hi_sorted is permuted along with idx.
 // A run longer than RS_TIE_CAP (thousands of particles inside one 2^-16 Boxsize cell, or exact
-// duplicates) would make that O(L^2) on one thread: it is left alone and reported through
-// n_tied[1], which the step turns into an error instead of an apparent hang.
+// duplicates) would make that O(L^2) on one thread: it is recorded in `long_runs` and sorted by
+// a whole block in k_fix_long_ties (bitonic network, O(L log^2 L)).  n_tied: [0] particles in
+// runs, [1] set when more than RS_LONG_CAP long runs exist (an error), [2] long runs recorded.
 #define RS_TIE_CAP 256
+#define RS_LONG_CAP 1024
 __global__ void k_fix_ties(int n, uint64_t *__restrict__ hi_sorted, int *__restrict__ idx,
-                           const uint64_t *__restrict__ key_lo, int low_bits, int *__restrict__ n_tied)
+                           const uint64_t *__restrict__ key_lo, int low_bits, int *__restrict__ n_tied,
+                           int2 *__restrict__ long_runs)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -223,7 +226,12 @@ __global__ void k_fix_ties(int n, uint64_t *__restrict__ hi_sorted, int *__restr
     int end = k + 1;
     while (end < n && (hi_sorted[end] >> low_bits) == h) end++;
     atomicAdd(n_tied, end - k);
-    if (end - k > RS_TIE_CAP) { atomicMax(n_tied + 1, end - k); return; }
+    if (end - k > RS_TIE_CAP) {
+        const int slot = atomicAdd(n_tied + 2, 1);
+        if (slot < RS_LONG_CAP) long_runs[slot] = make_int2(k, end);
+        else atomicMax(n_tied + 1, end - k);
+        return;
+    }
     for (int a = k + 1; a < end; a++) {
         const int ia = idx[a];
         const uint64_t ha = hi_sorted[a], la = key_lo[ia];
@@ -238,5 +246,52 @@ __global__ void k_fix_ties(int n, uint64_t *__restrict__ hi_sorted, int *__restr
         }
         idx[b + 1] = ia;
         hi_sorted[b + 1] = ha;
+    }
+}
+
+// The long runs k_fix_ties left: one block per run, bitonic sorting network on (key_hi, key_lo,
+// index) in global memory.  Every merge is ascending (first step of a stage mirrors the upper
+// half, partner = i ^ (size - 1)), so the virtual +inf pad of a run that is no power of two
+// never moves and pairs that reach into it are skipped.  Launched every step; without long runs
+// the blocks return at once.
+__global__ void __launch_bounds__(1024) k_fix_long_ties(uint64_t *__restrict__ hi_sorted, int *__restrict__ idx,
+                                                        const uint64_t *__restrict__ key_lo,
+                                                        const int *__restrict__ n_tied,
+                                                        const int2 *__restrict__ long_runs)
+{
+    const int nruns = min(n_tied[2], RS_LONG_CAP);
+    for (int r = blockIdx.x; r < nruns; r += gridDim.x) {
+        const int k = long_runs[r].x, L = long_runs[r].y - long_runs[r].x;
+        uint64_t *h = hi_sorted + k;
+        int *ix = idx + k;
+        auto cmpswap = [&](int i, int j) {               // i < j < L: smaller element to i
+            const uint64_t hi_i = h[i], hi_j = h[j];
+            const int ii = ix[i], ij = ix[j];
+            bool swap = hi_j < hi_i;
+            if (hi_j == hi_i) {
+                const uint64_t li = key_lo[ii], lj = key_lo[ij];
+                swap = lj < li || (lj == li && ij < ii);
+            }
+            if (swap) { h[i] = hi_j; h[j] = hi_i; ix[i] = ij; ix[j] = ii; }
+        };
+        int P = 1;
+        while (P < L) P <<= 1;
+        for (int size = 2; size <= P; size <<= 1) {
+            const int half = size >> 1;
+            for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                const int blk = t / half, off = t - blk * half;
+                const int i = blk * size + off, j = blk * size + size - 1 - off;
+                if (j < L) cmpswap(i, j);
+            }
+            __syncthreads();
+            for (int stride = half >> 1; stride >= 1; stride >>= 1) {
+                for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+                    const int i = (t / stride) * 2 * stride + (t % stride), j = i + stride;
+                    if (j < L) cmpswap(i, j);
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
     }
 }

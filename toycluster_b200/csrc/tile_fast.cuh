@@ -44,21 +44,39 @@
 // flight per SM instead of three and fewer warps waiting at each tile boundary (measured at
 // 10 M: 55.7 vs 56.4 ms per step; 8 x 4 at 64 registers 61.9, 12 x 2 60.0, 8 x 2 72.0).
 #ifndef TF_WARPS
-#define TF_WARPS 6
+#define TF_WARPS 5
 #endif
 #ifndef TF_BLOCKS
-#define TF_BLOCKS 4
+#define TF_BLOCKS 5
 #endif
 
-// Shared memory: bit matrix, run list, per warp a hit list (particle indices) and a float
-// separation list, per-warp statistics.
-#define TF_OFF_MASK 0
-#define TF_OFF_RUN (TF_OFF_MASK + TL_WORDS * TL_MSTRIDE * 4)
-#define TF_OFF_UL (TF_OFF_RUN + TL_RUNS * 4)
-#define TF_OFF_RL (TF_OFF_UL + TF_WARPS * TL_CAP * 4)
-#define TF_OFF_MISC (TF_OFF_RL + TF_WARPS * TL_CAP * 4)
-#define TF_OFF_CNT (TF_OFF_MISC + 64)
-#define TF_SMEM (TF_OFF_CNT + TF_WARPS * 32)
+// Tiles in flight per block.  The bit matrix of a tile lives in a block-private stretch of
+// global memory (L2 resident: 16 KB per tile), so that TF_NB of them cost no shared memory and
+// the warps of a block need no common barrier: a warp that finds no target left in tile t goes
+// on to the run list / phase 1 / targets of tile t+1 while the others finish (see the kernel).
+#ifndef TF_NB
+#define TF_NB 2
+#endif
+// hits within R_i / density list entries per target (a multiple of 64; < NGBMAX, so the list cut
+// of tree.c:91-92 cannot bite).  With the bit matrix out of shared memory the lists are what is left.
+#ifndef TF_CAP
+#define TF_CAP 896
+#endif
+#ifndef TF_P1_CHUNK
+#define TF_P1_CHUNK 4
+#endif
+#define TF_MASK_WORDS (TL_WORDS * 32)    // per tile: [word][target]
+
+// Shared memory: run lists of the tiles in flight, per warp a hit list (particle indices) and a
+// float separation list, the tile pipeline's control words, per-warp statistics.
+#define TF_OFF_RUN 0
+#define TF_OFF_UL (TF_OFF_RUN + TF_NB * TL_RUNS * 4)
+#define TF_OFF_RL (TF_OFF_UL + TF_WARPS * TF_CAP * 4)
+#define TF_OFF_MISC (TF_OFF_RL + TF_WARPS * TF_CAP * 4)
+#define TF_OFF_CNT (TF_OFF_MISC + 256)
+#define TF_OFF_FL (TF_OFF_CNT + TF_WARPS * 32)
+#define TF_FLAG_CAP 32                   // per warp: hits underneath displaced nodes, kept for the second pass
+#define TF_SMEM (TF_OFF_FL + TF_WARPS * TF_FLAG_CAP * 4)
 
 #define TF_KW (1365.0 / (64 * K_PI))
 
@@ -73,6 +91,21 @@ static __device__ __forceinline__ float rsqrt_approx(float x)
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// 256-bit read-only load (LDG.E.256 on sm_100a): the 32-byte pair record of the packed phase 2
+// and the eight-float rows of phase 1 in one request instead of two.
+struct __align__(32) u256 { unsigned long long a, b, c, d; };
+static __device__ __forceinline__ u256 ldg256(const void *p)
+{
+    u256 r;
+#ifdef TF_NO_LDG256
+    const ulonglong2 lo = __ldg((const ulonglong2 *)p), hi = __ldg((const ulonglong2 *)p + 1);
+    r.a = lo.x; r.b = lo.y; r.c = hi.x; r.d = hi.y;
+#else
+    asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
+#endif
+    return r;
 }
 
 // Closest-image separation xi - xj -+ Boxsize, accurate in float.  The reference's neighbour
@@ -205,21 +238,68 @@ static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const 
     return done;
 }
 
+// Phase 1 for the bit-matrix words [q0, q1) of this lane's target (four runs of eight candidates
+// per word): tile.cuh's tile_phase1 with the words handed out by ticket instead of by warp
+// number, and software-pipelined -- the three rows of run r + 1 are in flight while run r is
+// tested (ncu: the first use of the rows held 19 % of the kernel's stall samples when every run
+// waited for its own loads).
+template <bool INTERIOR>
+static __device__ __forceinline__ void tf_phase1_words(const float *__restrict__ sx, const float *__restrict__ sy,
+                                                       const float *__restrict__ sz, const int *s_run, int q0, int q1,
+                                                       int nruns, f32x2 xi2, f32x2 yi2, f32x2 zi2, float R2p, float box,
+                                                       unsigned *__restrict__ gmask_lane)
+{
+    const float ibox = 1.f / box;
+    const f32x2 ib2 = pack2(ibox, ibox), mg2 = pack2(12582912.f, 12582912.f);
+    const f32x2 nb2 = pack2(-box, -box);
+    const int rend = min(4 * q1, nruns);     // runs [4 q0, rend)
+    int first = s_run[4 * q0];               // multiple of 8: 32-byte aligned rows
+    // same address in every lane: broadcast loads of whole rows
+    u256 X = ldg256(sx + first), Y = ldg256(sy + first), Z = ldg256(sz + first);
+    unsigned word = 0;
+#pragma unroll 1
+    for (int r = 4 * q0; r < rend; r++) {
+        const int nfirst = s_run[min(r + 1, rend - 1)];       // (past the end: re-read, unused)
+        const u256 Xn = ldg256(sx + nfirst), Yn = ldg256(sy + nfirst), Zn = ldg256(sz + nfirst);
+        unsigned sub = 0;
+        auto test2 = [&](f32x2 A, f32x2 B, f32x2 C, unsigned b0, unsigned b1) {
+            f32x2 dx = sub2(xi2, A), dy = sub2(yi2, B), dz = sub2(zi2, C);
+            if (!INTERIOR) {
+                dx = fma2(sub2(fma2(dx, ib2, mg2), mg2), nb2, dx);
+                dy = fma2(sub2(fma2(dy, ib2, mg2), mg2), nb2, dy);
+                dz = fma2(sub2(fma2(dz, ib2, mg2), mg2), nb2, dz);
+            }
+            float s0, s1;
+            unpack2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), s0, s1);
+            if (s0 < R2p) sub |= b0;
+            if (s1 < R2p) sub |= b1;
+        };
+        test2(X.a, Y.a, Z.a, 1u, 2u);
+        test2(X.b, Y.b, Z.b, 4u, 8u);
+        test2(X.c, Y.c, Z.c, 16u, 32u);
+        test2(X.d, Y.d, Z.d, 64u, 128u);
+        word |= sub << (8 * (r & 3));        // the pad of a short last run is far away
+        if ((r & 3) == 3 || r == rend - 1) {
+            gmask_lane[(r >> 2) * 32] = word;
+            word = 0;
+        }
+        X = Xn; Y = Yn; Z = Zn;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(const SweepArgs a, int tile_lo,
                                                                         int tile_hi)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned *s_mask = (unsigned *)(smem + TF_OFF_MASK);
-    int *s_run = (int *)(smem + TF_OFF_RUN);        // first particle of each candidate run
-    int *s_misc = (int *)(smem + TF_OFF_MISC);       // [0] tile, [1] next target
     unsigned long long *s_cnt = (unsigned long long *)(smem + TF_OFF_CNT);   // per warp: evals, gathered, searches, iters
 
     const int lane = lane_id();
     const int w = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1;
-    int *ul = (int *)(smem + TF_OFF_UL) + w * TL_CAP;          // hit list: particle indices
-    float *rl = (float *)(smem + TF_OFF_RL) + w * TL_CAP;
+    int *ul = (int *)(smem + TF_OFF_UL) + w * TF_CAP;          // hit list: particle indices
+    float *rl = (float *)(smem + TF_OFF_RL) + w * TF_CAP;
+    int *fl = (int *)(smem + TF_OFF_FL) + w * TF_FLAG_CAP;     // flagged hits of the current target
     unsigned long long *cw = s_cnt + w * 4;
     if (lane < 4) cw[lane] = 0;
 
@@ -234,75 +314,142 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
         }
     };
 
-    for (;;) {
-        __syncthreads();              // previous tile fully consumed
-        if (threadIdx.x == 0) { s_misc[0] = atomicAdd(a.next, 1); s_misc[1] = 0; }
-        __syncthreads();
-        const int tile = tile_lo + s_misc[0];
-        if (tile >= tile_hi) break;
-        const int code = a.tile_ng[tile];
-        if (code < 0) {               // whole tile to the generic path
-            if (w == 0) {
-                const int i = tile * 32 + lane;
-                if (i < n) {
-                    a.worklist[atomicAdd(a.nwork, 1)] = i;
-                    atomicAdd(&a.counters[4], 1ull);
+    // ---- the tile pipeline ---------------------------------------------------------------
+    // Every warp walks the block's tile sequence t = 0, 1, 2, ... on its own; tile t uses buffer
+    // t % TF_NB (run list in shared memory, bit matrix in global).  Per buffer:
+    //   CLAIM   t+1 of the last tile claimed: the FIRST warp to arrive at t fetches the tile and
+    //           builds its run list -- after every warp has LEFT the tile that used the buffer
+    //           before (LEFT is cumulative: TF_WARPS per tile) -- then publishes READY = t+1;
+    //   P1NEXT / P1DONE   phase 1 in tickets of TF_P1_CHUNK bit-matrix words, taken by whichever
+    //           warps are there; everybody waits until all words are written;
+    //   TNEXT   phase 2: the targets, one ticket per target as before.
+    // Fast warps therefore run ahead by up to TF_NB - 1 tiles instead of idling at a block
+    // barrier while the last targets of a tile are finished (round 2 ncu: 9 % of the warp time).
+    enum { C_TILE = 0, C_CODE, C_READY, C_CLAIM, C_LEFT, C_P1NEXT, C_P1DONE, C_TNEXT, C_STRIDE };
+    static_assert(TF_NB * C_STRIDE * 4 <= 256, "control words");
+    int *s_ctl = (int *)(smem + TF_OFF_MISC);
+    if (threadIdx.x < TF_NB * C_STRIDE) s_ctl[threadIdx.x] = 0;
+    __syncthreads();                           // the only block barrier of the kernel
+    unsigned *gm_block = a.tile_mask + (size_t)blockIdx.x * (TF_NB * TF_MASK_WORDS);
+
+    auto wait_for = [&](const int *p, int need) {            // lane 0 polls, the warp follows
+        if (lane == 0)
+            while (*(volatile const int *)p < need) __nanosleep(40);
+        __syncwarp();
+        __threadfence_block();
+    };
+
+    for (int t = 0;; t++) {
+        const int b = t % TF_NB;
+        int *ctl = s_ctl + b * C_STRIDE;
+        int *s_run = (int *)(smem + TF_OFF_RUN) + b * TL_RUNS;       // first particle of each candidate run
+        unsigned *gmask = gm_block + b * TF_MASK_WORDS;
+        auto leave = [&]() {                   // this warp is done with the buffer
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicAdd(&ctl[C_LEFT], 1);
+        };
+
+        int first = 0;
+        if (lane == 0) first = atomicMax(&ctl[C_CLAIM], t + 1) <= t;
+        first = __shfl_sync(FULL_MASK, first, 0);
+        if (first) {
+            wait_for(&ctl[C_LEFT], TF_WARPS * (t / TF_NB));
+            int tl = 0;
+            if (lane == 0) tl = atomicAdd(a.next, 1);
+            tl = tile_lo + __shfl_sync(FULL_MASK, tl, 0);
+            int cd = 0;
+            if (tl >= tile_hi) tl = -1;
+            else {
+                cd = a.tile_ng[tl];
+                if (cd < 0) {                  // whole tile to the generic path
+                    const int i = tl * 32 + lane;
+                    if (i < n) {
+                        a.worklist[atomicAdd(a.nwork, 1)] = i;
+                        atomicAdd(&a.counters[4], 1ull);
+                    }
+                } else {
+                    // ---- candidate runs of the tile (ascending) ----------------------------------
+                    const int nent = cd & 0xfff, nruns = (cd >> 12) & 0xffff;
+                    const int *ent = a.tile_groups + (size_t)tl * TL_ENT;
+                    int base = 0;
+                    for (int e0 = 0; e0 < nent; e0 += 32) {
+                        const int e = e0 + lane;
+                        const int v = e < nent ? ent[e] : 0;
+                        const int c = __popc(v & 0xf);
+                        int incl = c;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int u = __shfl_up_sync(FULL_MASK, incl, o);
+                            if (lane >= o) incl += u;
+                        }
+                        int off = base + incl - c;
+                        for (int bb = 0; bb < 4; bb++)
+                            if (v & (1 << bb)) s_run[off++] = (v >> 4) * 32 + 8 * bb;
+                        base += __shfl_sync(FULL_MASK, incl, 31);
+                    }
+                    // pad to a whole word of four runs (the expansion reads them four at a time)
+                    const int ngp = (nruns + 3) >> 2;
+                    if (lane < 4 && base + lane < 4 * ngp) s_run[base + lane] = 0;
                 }
             }
-            continue;
-        }
-        const int nent = code & 0xfff, nruns = (code >> 12) & 0xffff;
+            if (lane == 0) { ctl[C_TILE] = tl; ctl[C_CODE] = cd; ctl[C_P1NEXT] = 0; ctl[C_P1DONE] = 0; ctl[C_TNEXT] = 0; }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *(volatile int *)&ctl[C_READY] = t + 1;
+        } else
+            wait_for(&ctl[C_READY], t + 1);
+
+        const int tile = *(volatile int *)&ctl[C_TILE];
+        if (tile < 0) break;                   // no tiles left: every warp sees this at the same t
+        const int code = *(volatile int *)&ctl[C_CODE];
+        if (code < 0) { leave(); continue; }
+        const int nruns = (code >> 12) & 0xffff;
         const int ng = (nruns + 3) >> 2;           // bit-matrix words
         const bool interior = (code >> 30) & 1;
 
-        // ---- candidate runs of the tile (ascending) --------------------------------------
-        if (w == 0) {
-            const int *ent = a.tile_groups + (size_t)tile * TL_ENT;
-            int base = 0;
-            for (int e0 = 0; e0 < nent; e0 += 32) {
-                const int e = e0 + lane;
-                const int v = e < nent ? ent[e] : 0;
-                const int c = __popc(v & 0xf);
-                int incl = c;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(FULL_MASK, incl, o);
-                    if (lane >= o) incl += u;
-                }
-                int off = base + incl - c;
-                for (int b = 0; b < 4; b++)
-                    if (v & (1 << b)) s_run[off++] = (v >> 4) * 32 + 8 * b;
-                base += __shfl_sync(FULL_MASK, incl, 31);
-            }
-            // pad to a whole word of four runs (the expansion reads them four at a time)
-            if (lane < 4 && base + lane < 4 * ng) s_run[base + lane] = 0;
-        }
-        __syncthreads();
-
         // ---- phase 1: lane = target, superset bit matrix at radius R_i (tile.cuh) --------
         {
-            const int i = tile * 32 + lane;
-            float xi = 0, yi = 0, zi = 0, R2 = -1.f;
-            if (i < n) {
-                const float4 pi = a.pw[i];
-                xi = pi.x; yi = pi.y; zi = pi.z;
-                const float R = tile_radius(a.hsml_in[i], pi.w, norm, a.bx.box_d, (MODE & MODE_ROTA) ? 1 : 0);
-                R2 = __fmul_rn(R, R);
-            }
+            bool loaded = false;
+            float R2p = -1.f;
+            f32x2 xi2 = pack2(0.f, 0.f), yi2 = xi2, zi2 = xi2;
             const size_t n8 = ((size_t)n + 7) & ~(size_t)7;      // stride of the SoA copy
-            if (interior) tile_phase1<true, TF_WARPS>(a.soa, a.soa + n8, a.soa + 2 * n8, s_run, s_mask, w, lane, ng, nruns, xi, yi, zi, R2, box);
-            else tile_phase1<false, TF_WARPS>(a.soa, a.soa + n8, a.soa + 2 * n8, s_run, s_mask, w, lane, ng, nruns, xi, yi, zi, R2, box);
+            for (;;) {
+                int q0 = 0;
+                if (lane == 0) q0 = atomicAdd(&ctl[C_P1NEXT], TF_P1_CHUNK);
+                q0 = __shfl_sync(FULL_MASK, q0, 0);
+                if (q0 >= ng) break;
+                if (!loaded) {
+                    loaded = true;
+                    const int i = tile * 32 + lane;
+                    if (i < n) {
+                        const float4 pi = a.pw[i];
+                        xi2 = pack2(pi.x, pi.x); yi2 = pack2(pi.y, pi.y); zi2 = pack2(pi.z, pi.z);
+                        const float R = tile_radius(a.hsml_in[i], pi.w, norm, a.bx.box_d, (MODE & MODE_ROTA) ? 1 : 0);
+                        R2p = __fmul_rn(R, R) * 1.000002f;
+                    }
+                }
+                const int q1 = min(q0 + TF_P1_CHUNK, ng);
+                if (interior) tf_phase1_words<true>(a.soa, a.soa + n8, a.soa + 2 * n8, s_run, q0, q1, nruns, xi2, yi2, zi2, R2p, box, gmask + lane);
+                else tf_phase1_words<false>(a.soa, a.soa + n8, a.soa + 2 * n8, s_run, q0, q1, nruns, xi2, yi2, zi2, R2p, box, gmask + lane);
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) atomicAdd(&ctl[C_P1DONE], q1 - q0);
+            }
+            wait_for(&ctl[C_P1DONE], ng);
         }
-        __syncthreads();
 
         // ---- phase 2: one warp per target ------------------------------------------------
         for (;;) {
             int tsel = 0;
-            if (lane == 0) tsel = atomicAdd(&s_misc[1], 1);
+            if (lane == 0) tsel = atomicAdd(&ctl[C_TNEXT], 1);
             tsel = __shfl_sync(FULL_MASK, tsel, 0);
             if (tsel >= 32) break;
             const int i = tile * 32 + tsel;
             if (i >= n) continue;
+            // the target's own record and Hsml: in flight while the row is expanded
+            const float4 pi_raw = a.pw[i];
+            const float hA_in = a.hsml_in[i];
 
             // (1) expand the bit row into a compact list of particle indices.  Every lane owns
             //     the words lane, lane+32, ... of the row and writes their hits to one contiguous
@@ -319,7 +466,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
 #pragma unroll
             for (int j = 0; j < NW; j++) {
                 const int q = j * 32 + lane;
-                unsigned word = q < ng ? s_mask[q * TL_MSTRIDE + tsel] : 0u;
+                unsigned word = q < ng ? __ldcg(gmask + q * 32 + tsel) : 0u;
                 chits += __popc(word);
                 if (PAIRS) word = (word | (word >> 1)) & 0x55555555u;
                 wd[j] = word;
@@ -333,7 +480,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
             }
             const int nU = __shfl_sync(FULL_MASK, incl, 31);
             // the separation list must hold every hit: the same bound as in tile.cuh
-            if ((PAIRS ? __reduce_add_sync(FULL_MASK, chits) : nU) > TL_UCAP) { hand_back(i, 1); continue; }
+            if ((PAIRS ? __reduce_add_sync(FULL_MASK, chits) : nU) > TF_CAP) { hand_back(i, 1); continue; }
             {
                 int *out = ul + (incl - c);
 #pragma unroll
@@ -359,13 +506,20 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 if (nU + lane < ((nU + 31) & ~31)) ul[nU + lane] = PAIRS ? i >> 1 : i;
             }
             __syncwarp();
+            // the gather of the first batch starts now, ahead of the per-target constants
+            constexpr bool PAIRS_ = !(MODE & MODE_ROTA);
+            int g0 = ul[lane];                       // (nU >= 1: the target itself is a hit)
+            u256 P0;
+            float4 p0;
+            if (PAIRS_) P0 = ldg256((const u256 *)a.pwp + g0);
+            else p0 = a.pw[g0];
 
-            float4 pi = a.pw[i];
+            float4 pi = pi_raw;
             pi.w = fabsf(pi.w);                    // the sign bit is the displaced-node flag
             float hA2, hB2, hsw2, Afy, cn;
             float ax_i = 0, ay_i = 0, az_i = 0, inv_h = 0;        // rot(A): Apot_i, 1/Hsml
             if (MODE & MODE_ROTA) {
-                const float hA = a.hsml_in[i];
+                const float hA = hA_in;
                 hA2 = __fmul_rn(hA, hA); hB2 = hA2; hsw2 = 0; cn = 0;
                 inv_h = __frcp_rn(hA);
                 const float h2 = hA * hA;
@@ -373,7 +527,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 Afy = (float)(-a.bx.mpart / (double)a.rho_in[i] * (double)a.varh_in[i] * (TF_KW * -22.0) / ((double)h2 * (double)h2));
                 ax_i = a.apot[3 * (size_t)i]; ay_i = a.apot[3 * (size_t)i + 1]; az_i = a.apot[3 * (size_t)i + 2];
             } else {
-                const float hA = a.hsml_in[i];
+                const float hA = hA_in;
                 const float hB = (float)((double)hA * 1.23);                      // sph.c:51
                 const float hi_w = __fmul_rn(pi.w, norm);                         // wvt_relax.c:124
                 const float hsw = (float)((double)hi_w * a.bx.box_d);             // wvt_relax.c:135
@@ -390,10 +544,11 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
             //     only" from the back); displacement summed in place.  Hits underneath a displaced
             //     reference node (defect.cuh; ~1e-4 of the particles) are skipped by the hot loop
             //     and taken by a second pass with the open tests, so that the hot loop has no call.
-            int cntA = 0, baseB = TL_CAP - 1, cntW = 0, npair = 0;   // cntW, npair: per-lane until reduced
+            int cntA = 0, baseB = TF_CAP - 1, cntW = 0, npair = 0;   // cntW, npair: per-lane until reduced
             float sx = 0, sy = 0, sz = 0;
             bool sawflag = false;
-            auto batch = [&](const int k, const int gidx, const float4 pj, auto slow_tag) {
+            int nflag = 0;                         // flagged hits met by the packed pass (warp-uniform)
+            auto batch = [&](const bool live, const int gidx, const float4 pj, auto slow_tag) {
                 constexpr bool SLOW = decltype(slow_tag)::value;
                 const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
                 float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
@@ -412,7 +567,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 }
                 const bool flagged = df_flagged(pj.w);
                 // dead lanes: the pad of the last batch, and the hits the other pass takes
-                r2 = (k < nU && flagged == SLOW) ? r2 : 3.0e38f;
+                r2 = (live && flagged == SLOW) ? r2 : 3.0e38f;
                 bool inA = r2 < hA2, inB = r2 < hB2, inW = r2 < hsw2;
                 if (!SLOW) sawflag |= flagged;
                 if (SLOW && (inB | inW)) {
@@ -454,7 +609,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     cntW += inA;                                                 // gathered: the Hsml set
                 }
                 if (MODE & MODE_WVT) {
-                    // wvt_relax.c:137-170; nU <= TL_CAP < NGBMAX: the list cut cannot bite
+                    // wvt_relax.c:137-170; nU <= TF_CAP < NGBMAX: the list cut cannot bite
                     const float hp = (pi.w + fabsf(pj.w)) * cn;                   // :158, length units
                     const float u = fminf(r * rcp_approx(hp), 1.f);               // :160 skip <=> W = 0
                     const float t = 1.f - u, t2 = t * t, t4 = t2 * t2;
@@ -507,7 +662,13 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 const bool fl0 = df_flagged(w0), fl1 = df_flagged(w1);
                 r20 = (live && !fl0) ? r20 : 3.0e38f;       // dead: the pad, hits of the second pass;
                 r21 = (live && !fl1) ? r21 : 3.0e38f;       // (the pad of an odd n is finite and far away)
-                sawflag |= live && (fl0 | fl1);
+                if (__any_sync(FULL_MASK, live && (fl0 | fl1))) {       // rare: remember them for the second pass
+                    const unsigned m0 = __ballot_sync(FULL_MASK, live && fl0), m1 = __ballot_sync(FULL_MASK, live && fl1);
+                    const int p0 = nflag + __popc(m0 & lt), p1 = nflag + __popc(m0) + __popc(m1 & lt);
+                    if (live && fl0 && p0 < TF_FLAG_CAP) fl[p0] = 2 * pidx;
+                    if (live && fl1 && p1 < TF_FLAG_CAP) fl[p1] = 2 * pidx + 1;
+                    nflag += __popc(m0) + __popc(m1);
+                }
                 const bool inA0 = r20 < hA2, inB0 = r20 < hB2, inW0 = r20 < hsw2;
                 const bool inA1 = r21 < hA2, inB1 = r21 < hB2, inW1 = r21 < hsw2;
                 // r = sqrt(r2): MUFU.RSQ and one Newton step
@@ -558,51 +719,55 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
             if (PAIRS) {
                 // the gather of the next batch is in flight while this one is evaluated (two batches
                 // per trip, so the hand-over needs no register moves)
-                const ulonglong2 *pp = (const ulonglong2 *)a.pwp;
+                const u256 *pp = (const u256 *)a.pwp;    // one 32-byte record per pair
                 const int kend = nU + lane;
-                int g0 = ul[lane];                       // (nU >= 1: the target itself is a hit)
-                ulonglong2 A0 = pp[2 * (size_t)g0], B0 = pp[2 * (size_t)g0 + 1];
                 for (int k = lane; k < kend; k += 64) {
                     const int k1 = k + 32 < kend ? k + 32 : k;       // (past the end: re-read, unused)
                     const int g1 = ul[k1];
-                    const ulonglong2 A1 = pp[2 * (size_t)g1], B1 = pp[2 * (size_t)g1 + 1];
-                    batch2(k, g0, A0, B0);
+                    const u256 P1 = ldg256(pp + g1);
+                    batch2(k, g0, make_ulonglong2(P0.a, P0.b), make_ulonglong2(P0.c, P0.d));
                     const int k2 = k + 64 < kend ? k + 64 : k;
                     g0 = ul[k2];
-                    A0 = pp[2 * (size_t)g0]; B0 = pp[2 * (size_t)g0 + 1];
-                    if (k + 32 < kend) batch2(k + 32, g1, A1, B1);
+                    P0 = ldg256(pp + g0);
+                    if (k + 32 < kend) batch2(k + 32, g1, make_ulonglong2(P1.a, P1.b), make_ulonglong2(P1.c, P1.d));
                 }
                 float a0, a1;
                 unpack2(sx2, a0, a1); sx = a0 + a1;
                 unpack2(sy2, a0, a1); sy = a0 + a1;
                 unpack2(sz2, a0, a1); sz = a0 + a1;
-                if (__any_sync(FULL_MASK, sawflag))      // the flagged halves, one at a time
-                    for (int k = lane; k < nU + lane; k += 32) {
-                        const int g = 2 * ul[k];
-                        batch(k, g, a.pw[g], std::true_type{});
-                        batch(k, g + 1, a.pw[g + 1], std::true_type{});
-                    }
+                if (nflag > 0) {                          // the flagged hits, with the open tests
+                    __syncwarp();
+                    if (nflag <= TF_FLAG_CAP)
+                        for (int k = lane; k < nflag + lane; k += 32) {
+                            const int g = k < nflag ? fl[k] : i;
+                            batch(k < nflag, g, a.pw[g], std::true_type{});
+                        }
+                    else                                  // more than the list holds: rescan every pair
+                        for (int k = lane; k < nU + lane; k += 32) {
+                            const int g = 2 * ul[k];
+                            batch(k < nU, g, a.pw[g], std::true_type{});
+                            batch(k < nU, g + 1, a.pw[g + 1], std::true_type{});
+                        }
+                }
             } else {
                 const int kend = nU + lane;
-                int g0 = ul[lane];
-                float4 p0 = a.pw[g0];
                 for (int k = lane; k < kend; k += 64) {
                     const int k1 = k + 32 < kend ? k + 32 : k;
                     const int g1 = ul[k1];
                     const float4 p1 = a.pw[g1];
-                    batch(k, g0, p0, std::false_type{});
+                    batch(k < nU, g0, p0, std::false_type{});
                     const int k2 = k + 64 < kend ? k + 64 : k;
                     g0 = ul[k2];
                     p0 = a.pw[g0];
-                    if (k + 32 < kend) batch(k + 32, g1, p1, std::false_type{});
+                    if (k + 32 < kend) batch(k + 32 < nU, g1, p1, std::false_type{});
                 }
                 if (__any_sync(FULL_MASK, sawflag))
                     for (int k = lane; k < nU + lane; k += 32) {
                         const int g = ul[k];
-                        batch(k, g, a.pw[g], std::true_type{});
+                        batch(k < nU, g, a.pw[g], std::true_type{});
                     }
             }
-            const int cntBo = TL_CAP - 1 - baseB;
+            const int cntBo = TF_CAP - 1 - baseB;
             cntW = __reduce_add_sync(FULL_MASK, cntW);
             __syncwarp();
 
@@ -611,14 +776,14 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
             unsigned n_search = (MODE & MODE_WVT) ? 1 : 0, n_evals = 0, n_iters = 0;
             if (MODE & MODE_DENSITY) {
                 // (3) the outer loop of sph.c:36-64, as far as the two prepared radii carry it
-                const float hA = a.hsml_in[i];
+                const float hA = hA_in;
                 bool ok = true;
                 if (cntA >= TG_DESNNGB) {                    // first search succeeds: Hsml list
                     cnt = cntA; h = hA; n_search += 1;
                 } else if (cntA + cntBo >= TG_DESNNGB) {     // second search, 1.23*Hsml
                     // bring the entries beyond Hsml next to the others (ascending: a write never
                     // lands on an entry that is still to be read)
-                    const int src0 = TL_CAP - cntBo;
+                    const int src0 = TF_CAP - cntBo;
                     for (int b = 0; b < cntBo; b += 32) {
                         const int q = b + lane;
                         const float v = q < cntBo ? rl[src0 + q] : 0.f;
@@ -630,7 +795,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 } else ok = false;                           // a third search: generic path
                 int why = 3;
                 if (ok) {
-                    // pad to whole passes of 64 (TL_CAP is a multiple of 64)
+                    // pad to whole passes of 64 (TF_CAP is a multiple of 64)
                     const int cnt64 = (cnt + 63) & ~63;
                     if (cnt + lane < cnt64) rl[cnt + lane] = 3.0e38f;
                     if (cnt + 32 + lane < cnt64) rl[cnt + 32 + lane] = 3.0e38f;
@@ -672,6 +837,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 cw[0] += n_evals + npair; cw[1] += max(cnt, cntW); cw[2] += n_search; cw[3] += n_iters;
             }
         }
+        leave();
     }
 
     if (lane == 0) {

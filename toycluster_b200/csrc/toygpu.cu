@@ -101,11 +101,14 @@ struct tg_ctx {
     int npartial = 0;
     double *scal = nullptr;         // [0] vsum, [1] err sum, [2] err max
     int *flags = nullptr;           // [0] next, [1] status, [2] range_err, [3] n_tied, [4] cold, [5] nwork, [6] next (work list),
-                                    // [7] stop (tg_regularise), [8] n_tied scratch, [9] longest unsorted tie run
+                                    // [7] stop (tg_regularise), [8] n_tied scratch, [9] more long tie runs than
+                                    // RS_LONG_CAP, [10] long tie runs (k_fix_long_ties)
+    int2 *tie_runs = nullptr;       // [RS_LONG_CAP] (first, end) of the long runs
     unsigned long long *counters = nullptr;   // 4
     double *gscratch = nullptr;
     int sweep_blocks = 0;
     int *tile_ng = nullptr, *tile_groups = nullptr, *worklist = nullptr;
+    unsigned *tile_mask = nullptr;  // bit matrices of the tiles in flight (tile_fast.cuh), fast_blocks * TF_NB of them
     int tile_blocks = 0, fast_blocks = 0, sweep_fast_blocks = 0;
     bool use_tiles = true;
 
@@ -249,6 +252,8 @@ extern "C" int tg_destroy(tg_ctx *c)
     if (c->ngb_scratch) cudaFree(c->ngb_scratch);
     if (c->halo_counts) cudaFree(c->halo_counts);
     if (c->out_order) cudaFree(c->out_order);
+    if (c->tile_mask) cudaFree(c->tile_mask);
+    if (c->tie_runs) cudaFree(c->tie_runs);
     void *ptrs[] = {c->posh, c->id, c->apot, c->stage, c->key_hi, c->key_lo, c->key_tmp, c->idx, c->idx_tmp,
                     c->hist, c->pw, c->pwp, c->soa, c->hsml_in, c->rho_model, c->rm_state, c->rm_state_s, c->id_s, c->key_lo_s, c->apot_s,
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->sub_mem, c->cpl,
@@ -433,6 +438,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     CUC(dmalloc(&c->defect.big, DF_BIG_CAP));
     CUC(dmalloc(&c->defect.nodes, c->defect.cap_nodes));
     CUC(dmalloc(&c->defect.dmap, n));
+    c->defect.pwp = c->pwp;
     CUC(cudaMemsetAsync(c->defect.counts, 0, 8 * sizeof(int), c->stream));
 
     CUC(dmalloc(&c->halos, MAX_HALOS));
@@ -441,6 +447,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     CUC(dmalloc(&c->scal, 4));
     CUC(cudaHostAlloc((void **)&c->hpin, sizeof(double) * (2 * nranks + 8), cudaHostAllocDefault));
     CUC(dmalloc(&c->flags, 12));
+    CUC(dmalloc(&c->tie_runs, RS_LONG_CAP));
     CUC(dmalloc(&c->counters, 12));
     CUC(cudaMemsetAsync(c->flags, 0, 12 * sizeof(int), c->stream));
     CUC(cudaMemsetAsync(c->counters, 0, 12 * sizeof(unsigned long long), c->stream));
@@ -496,6 +503,7 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
                                                           TF_WARPS * 32, TF_SMEM));
         if (per < 1) per = 1;
         c->fast_blocks = prop.multiProcessorCount * per;
+        CUC(dmalloc(&c->tile_mask, (size_t)c->fast_blocks * TF_NB * TF_MASK_WORDS));
     }
     {
         auto set = [&](const void *f) {
@@ -871,8 +879,11 @@ static int sort_keys(tg_ctx *c)
     }
     c->key_hi_s = kin;
     c->idx_s = iin;
-    CU(cudaMemsetAsync(c->flags + 8, 0, 2 * sizeof(int), c->stream));
-    k_fix_ties<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->idx_s, c->key_lo, low_bits, c->flags + 8);
+    CU(cudaMemsetAsync(c->flags + 8, 0, 3 * sizeof(int), c->stream));
+    k_fix_ties<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->idx_s, c->key_lo, low_bits, c->flags + 8,
+                                               c->tie_runs);
+    LAUNCH_CHECK();
+    k_fix_long_ties<<<32, 1024, 0, c->stream>>>(c->key_hi_s, c->idx_s, c->key_lo, c->flags + 8, c->tie_runs);
     LAUNCH_CHECK();
     return TG_OK;
 }
@@ -976,6 +987,7 @@ static SweepArgs sweep_args(tg_ctx *c, double step)
     a.nwork = c->flags + 5;
     a.tile_ng = c->tile_ng;
     a.tile_groups = c->tile_groups;
+    a.tile_mask = c->tile_mask;
     a.dmap = c->defect.dmap;
     a.dnodes = c->defect.nodes;
     return a;
@@ -1076,8 +1088,8 @@ static int check_flags(tg_ctx *c, bool swept = true)
         c->index_valid = false;
     }
     if (f[2]) return fail(c, TG_ERANGE, "particle position outside [0, Boxsize] (peano.c:130-132)");
-    if (tie) return fail(c, TG_ERANGE, "%d particles share one sort cell (coincident positions?): the tie fix-up "
-                         "stops at runs of %d; rerun with TOYGPU_FULL_SORT=1 or remove the duplicates", tie, RS_TIE_CAP);
+    if (tie) return fail(c, TG_ERANGE, "more than %d sort cells hold over %d particles each (the longest %d; coincident "
+                         "positions?): rerun with TOYGPU_FULL_SORT=1 or remove the duplicates", RS_LONG_CAP, RS_TIE_CAP, tie);
     if (swept && dc[2] && !(c->cfg.flags & TG_EXACT_NEIGHBOURS))
         return fail(c, TG_ERANGE, "more displaced reference-tree nodes than the path table holds (%d events): the "
                          "neighbour sets would silently stop being the reference's; use TG_EXACT_NEIGHBOURS "
@@ -1153,6 +1165,10 @@ static int finish_stats(tg_ctx *c, bool have_sweep_events)
     if (have_sweep_events) {
         CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
         c->stats.sweep_ms = ms;
+        CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[2]));
+        c->stats.index_ms = ms;
+        CU(cudaEventElapsedTime(&ms, c->ev[3], c->ev[1]));
+        c->stats.tail_ms = ms;
     }
     return TG_OK;
 }
@@ -1509,6 +1525,8 @@ extern "C" int tg_get_stats(tg_ctx *c, tg_stats *out)
             t.hsml_iters += k.hsml_iters; t.kernels += k.kernels; t.handed_back += k.handed_back;
             for (int q = 0; q < 5; q++) t.handback_why[q] += k.handback_why[q];
             t.sweep_ms = std::max(t.sweep_ms, k.sweep_ms);
+            t.index_ms = std::max(t.index_ms, k.index_ms);
+            t.tail_ms = std::max(t.tail_ms, k.tail_ms);
             t.step_ms = std::max(t.step_ms, k.step_ms);
         }
         *out = t;
