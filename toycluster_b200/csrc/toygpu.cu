@@ -132,6 +132,12 @@ struct tg_ctx {
     std::vector<tg_ctx *> kids;
 
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // The displaced-node kernels (defect.cuh: one FP64-bound pass + latency-bound path walks of
+    // a few hundred particles) run on a side stream next to the box hierarchy and the tile walk
+    // and are joined before the first kernel that reads the flags / paths (join_defects).
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool defect_pending = false;
     tg_stats stats{};
     unsigned long long launches = 0;
 };
@@ -265,6 +271,9 @@ extern "C" int tg_destroy(tg_ctx *c)
     for (void *h : c->pinned) cudaHostUnregister(h);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
     return TG_OK;
 }
@@ -368,6 +377,9 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
     else { CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     for (auto &ev : c->ev) CUC(cudaEventCreate(&ev));
+    CUC(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 
     CUC(dmalloc(&c->posh, npad));
     CUC(dmalloc(&c->id, n));
@@ -847,6 +859,16 @@ static int reset_counters(tg_ctx *c)
     return TG_OK;
 }
 
+// The main stream waits for the displaced-node kernels of the current index (no-op when they
+// ran in line or were joined already).
+static int join_defects(tg_ctx *c)
+{
+    if (!c->defect_pending) return TG_OK;
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    c->defect_pending = false;
+    return TG_OK;
+}
+
 // peano.c:46-81 (keys, index sort) -- leaves key_hi_s / idx_s.
 static int sort_keys(tg_ctx *c)
 {
@@ -894,8 +916,9 @@ static int prepare_index(tg_ctx *c)
     const int n = c->n, T = 256;
     if (c->nhalos == 0) return fail(c, TG_EINVAL, "tg_set_halos has not been called");
     if (c->poisoned) return fail(c, TG_EINVAL, "the previous step failed half-way: upload the particles again");
-    int rc = sort_keys(c);
+    int rc = join_defects(c);            // (a previous index whose flags nobody read)
     if (rc) return rc;
+    if ((rc = sort_keys(c))) return rc;
 
     k_reorder_model<<<c->npartial, RED_THREADS, 0, c->stream>>>(
         n, c->idx_s, c->posh, c->id, c->key_lo, c->have_apot ? c->apot : nullptr, c->rm_state,
@@ -903,6 +926,38 @@ static int prepare_index(tg_ctx *c)
         c->id_s, c->rho_model, c->key_lo_s, c->apot_s, c->halos, c->nhalos, c->box.mpart,
         c->box.boxhalf_d, c->partial);
     LAUNCH_CHECK();
+
+    // tree.c:298-310: nodes displaced by the sign test, and what they prune.  Needs the sorted
+    // keys and positions only; nothing before the sweep reads its output (pw.w is read through
+    // fabsf by the tile walk), so it runs beside the hierarchy build unless the cold start needs
+    // cpl on the main stream anyway.
+    const bool emulate = !(c->cfg.flags & TG_EXACT_NEIGHBOURS);
+    const bool beside = emulate && !c->any_cold && !getenv("TOYGPU_NO_SIDE_STREAM");
+    cudaStream_t ds = beside ? c->side : c->stream;
+    if (beside) {
+        CU(cudaEventRecord(c->ev_fork, c->stream));
+        CU(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    }
+    if (c->any_cold || emulate) {
+        k_cpl<<<cdiv(n, T), T, 0, ds>>>(n, c->key_hi_s, c->key_lo_s, c->cpl);
+        LAUNCH_CHECK();
+    }
+    CU(cudaMemsetAsync(c->defect.counts, 0, 8 * sizeof(int), ds));
+    if (emulate) {
+        k_defect_detect<<<cdiv(n, T), T, 0, ds>>>(n, c->pw, c->box.box_d, c->cpl, c->defect);
+        LAUNCH_CHECK();
+        k_defect_paths<<<296, 128, 0, ds>>>(n, c->pw, c->box.box_d, c->key_hi_s, c->key_lo_s,
+                                                  c->cpl, c->defect);
+        LAUNCH_CHECK();
+        k_defect_paths_big<<<296, 128, 0, ds>>>(n, c->pw, c->box.box_d, c->key_hi_s,
+                                                      c->key_lo_s, c->cpl, c->defect);
+        LAUNCH_CHECK();
+    }
+    if (beside) {
+        CU(cudaEventRecord(c->ev_join, c->side));
+        c->defect_pending = true;
+    }
+
     k_final_sum<<<1, RED_THREADS, 0, c->stream>>>(c->npartial, c->partial, c->scal);
     LAUNCH_CHECK();
 
@@ -923,22 +978,6 @@ static int prepare_index(tg_ctx *c)
         LAUNCH_CHECK();
     }
 
-    const bool emulate = !(c->cfg.flags & TG_EXACT_NEIGHBOURS);
-    if (c->any_cold || emulate) {
-        k_cpl<<<cdiv(n, T), T, 0, c->stream>>>(n, c->key_hi_s, c->key_lo_s, c->cpl);
-        LAUNCH_CHECK();
-    }
-    CU(cudaMemsetAsync(c->defect.counts, 0, 8 * sizeof(int), c->stream));
-    if (emulate) {       // tree.c:298-310: nodes displaced by the sign test, and what they prune
-        k_defect_detect<<<cdiv(n, T), T, 0, c->stream>>>(n, c->pw, c->box.box_d, c->cpl, c->defect);
-        LAUNCH_CHECK();
-        k_defect_paths<<<296, 128, 0, c->stream>>>(n, c->pw, c->box.box_d, c->key_hi_s, c->key_lo_s,
-                                                  c->cpl, c->defect);
-        LAUNCH_CHECK();
-        k_defect_paths_big<<<296, 128, 0, c->stream>>>(n, c->pw, c->box.box_d, c->key_hi_s,
-                                                      c->key_lo_s, c->cpl, c->defect);
-        LAUNCH_CHECK();
-    }
     if (c->any_cold) {   // tree.c:113-121 stand-in for particles with Hsml == 0
         k_collapse_events<<<cdiv(n, T), T, 0, c->stream>>>(n, c->cpl, c->ev_start, c->ev_level, c->ev_count);
         LAUNCH_CHECK();
@@ -997,6 +1036,7 @@ static SweepArgs sweep_args(tg_ctx *c, double step)
 template <int MODE> static int launch_generic(tg_ctx *c, SweepArgs a)
 {
     const size_t smem = (size_t)SW_WARPS * SW_LCAP * sizeof(double);
+    { const int rc = join_defects(c); if (rc) return rc; }
     CU(cudaMemsetAsync(c->flags, 0, sizeof(int), c->stream));       // work counter
     a.next = c->flags;
     constexpr bool has_fast = MODE == MODE_DENSITY || MODE == (MODE_DENSITY | MODE_WVT);
@@ -1024,6 +1064,7 @@ template <int MODE> static int launch_tiled(tg_ctx *c, SweepArgs a)
         c->bvh, c->box, c->pw, a.hsml_in, c->scal, tile_lo, tile_hi, c->tile_ng, c->tile_groups,
         MODE == MODE_ROTA ? 1 : 0);
     LAUNCH_CHECK();
+    { const int rc = join_defects(c); if (rc) return rc; }
     a.next = c->flags;
     constexpr bool has_fast = MODE == MODE_DENSITY || MODE == (MODE_DENSITY | MODE_WVT) || MODE == MODE_ROTA;
     constexpr bool has_exact = MODE != MODE_ROTA;
@@ -1067,6 +1108,7 @@ template <int MODE> static int launch_sweep(tg_ctx *c, const SweepArgs &a)
 static int check_flags(tg_ctx *c, bool swept = true)
 {
     int f[10], dc[4];
+    { const int rc = join_defects(c); if (rc) return rc; }
     {   // a rank that fails must take the others with it, or their next collective hangs
         const int rc = reduce_flags_max(c, c->flags + 1, 2);
         if (rc) return rc;
@@ -1790,6 +1832,7 @@ extern "C" int tg_find_ngb(tg_ctx *c, int i, float h, int32_t *list, int *count)
     CU(cudaSetDevice(c->cfg.device));
     if (!c->ngb_scratch) CU(dmalloc(&c->ngb_scratch, TG_NGBMAX + 1));
     int *d = c->ngb_scratch;
+    { const int rc = join_defects(c); if (rc) return rc; }
     k_find_ngb<<<1, 32, 0, c->stream>>>(c->bvh, c->box, c->pw, i, h, c->defect.dmap, c->defect.nodes, d, d + TG_NGBMAX);
     c->launches++;
     cudaError_t e = cudaStreamSynchronize(c->stream);
