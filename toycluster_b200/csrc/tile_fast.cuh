@@ -40,14 +40,16 @@
 #include <type_traits>
 #include "tile.cuh"
 
-// 6 warps x 4 blocks per SM: the same 24 warps and 85-register budget as 8 x 3, four tiles in
-// flight per SM instead of three and fewer warps waiting at each tile boundary (measured at
-// 10 M: 55.7 vs 56.4 ms per step; 8 x 4 at 64 registers 61.9, 12 x 2 60.0, 8 x 2 72.0).
+// Block shape.  The kernel needs 72 registers, so 28 warps fit an SM; with the bit matrix out of
+// shared memory (below) the warps of a block share nothing but the run list, and small blocks
+// keep more tiles in flight: measured at 10 M (sweep incl. tile walk and hand-backs) 4 x 7:
+// 50.5 ms, 3 x 9: 50.6, 2 x 14: 50.2 (shorter hit lists), 7 x 4: 51.1, 5 x 5: 52.2, 6 x 4 at 80
+// registers: 52.9, 8 x 4 at 64 registers: 53.4, 12 x 2: 56.5, 24 x 1: 64.6.
 #ifndef TF_WARPS
-#define TF_WARPS 5
+#define TF_WARPS 4
 #endif
 #ifndef TF_BLOCKS
-#define TF_BLOCKS 5
+#define TF_BLOCKS 7
 #endif
 
 // Tiles in flight per block.  The bit matrix of a tile lives in a block-private stretch of
@@ -60,7 +62,7 @@
 // hits within R_i / density list entries per target (a multiple of 64; < NGBMAX, so the list cut
 // of tree.c:91-92 cannot bite).  With the bit matrix out of shared memory the lists are what is left.
 #ifndef TF_CAP
-#define TF_CAP 896
+#define TF_CAP 832
 #endif
 #ifndef TF_P1_CHUNK
 #define TF_P1_CHUNK 4
