@@ -1,12 +1,13 @@
-"""Group the per-line output of ncu_lines.py by code region of tile_fast.cuh: ncu_groups.py lines.txt <inst per 1%>"""
+"""Group the per-line output of ncu_lines.py by code region of tile_fast.cuh: ncu_groups.py lines.txt <inst per 1%> [source snapshot]"""
 import re, collections, sys
 per = float(sys.argv[2]) if len(sys.argv) > 2 else 42.0
-src = open('/root/repo/gpurun_out/r02h_tile_fast.cuh').read().splitlines()
+src = open(sys.argv[3] if len(sys.argv) > 3 else '/root/repo/gpurun_out/r02q_tile_fast.cuh').read().splitlines()
 def find(t): return [i + 1 for i, l in enumerate(src) if t in l][0]
 marks = [(find('static __device__ __forceinline__ float rcp_approx'), 'find_hsml_fast'),
-         (find('template <int MODE>'), 'kernel setup / tile loop'),
+         (find('static __device__ __forceinline__ void tf_phase1_words'), 'phase 1'),
+         (find('__global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast'), 'kernel setup / tile pipeline control'),
          (find('candidate runs of the tile'), 'run list'),
-         (find('phase 1: lane = target'), 'phase1 call'),
+         (find('phase 1: lane = target'), 'phase 1 tickets'),
          (find('phase 2: one warp per target'), 'phase2 setup'),
          (find('(1) expand the bit row'), 'expand'),
          (find('float4 pi = a.pw[i];'), 'target constants'),

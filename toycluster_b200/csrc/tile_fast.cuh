@@ -67,6 +67,9 @@
 #ifndef TF_P1_CHUNK
 #define TF_P1_CHUNK 4
 #endif
+#ifndef TF_POLL_NS
+#define TF_POLL_NS 40                    // a waiting warp looks at its control word this often
+#endif
 #define TF_MASK_WORDS (TL_WORDS * 32)    // per tile: [word][target]
 
 // Shared memory: run lists of the tiles in flight, per warp a hit list (particle indices) and a
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
 
     auto wait_for = [&](const int *p, int need) {            // lane 0 polls, the warp follows
         if (lane == 0)
-            while (*(volatile const int *)p < need) __nanosleep(40);
+            while (*(volatile const int *)p < need) __nanosleep(TF_POLL_NS);
         __syncwarp();
         __threadfence_block();
     };
