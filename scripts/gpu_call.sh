@@ -1,12 +1,2 @@
-python scripts/dbg_bfield_time.py merger_1e6 2>&1 | grep "step 0"
-TOYGPU_LIB=$PWD/toycluster_b200/variants/libtoygpu_0old.so python - <<'PY'
-import sys, time
-sys.path.insert(0, '.')
-import toycluster_b200 as tc
-from toycluster_b200 import workloads
-w = workloads.make("merger_1e6")
-g = tc.HotPath.from_workload(w, flags=tc.FAST)
-g.upload(w.pos)
-g.wvt_iteration(0.0085); s = g.stats()
-print("OLD step 0 step_ms %.1f sweep %.1f" % (s["step_ms"], s["sweep_ms"]))
-PY
+timeout 600 python scripts/time_variants.py > gpurun_out/variants12.log 2>&1; cat gpurun_out/variants12.log | cut -c1-200
+timeout 900 python -m pytest tests/test_gpu_fast.py -x -q -m gpu > gpurun_out/t_fast_p4.log 2>&1; tail -3 gpurun_out/t_fast_p4.log

@@ -98,6 +98,15 @@ static __device__ __forceinline__ float rsqrt_approx(float x)
     return y;
 }
 
+// 1 / x to ~4e-15: MUFU.RCP on the float of x and one Newton step in double.  For the FP64
+// quotients of the Find_hsml control flow (a correctly rounded FP64 divide is ~25 instructions
+// on every lane, and TG_FAST needs those quotients to ~1e-9 at most).
+static __device__ __forceinline__ double rcp_fast(double x)
+{
+    const double y = (double)rcp_approx((float)x);
+    return fma(y, fma(-x, y, 1.0), y);
+}
+
 // 256-bit read-only load (LDG.E.256 on sm_100a): the 32-byte pair record of the packed phase 2
 // and the eight-float rows of phase 1 in one request instead of two.
 struct __align__(32) u256 { unsigned long long a, b, c, d; };
@@ -156,6 +165,9 @@ static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const 
 
     double upper = (double)h_io * K_SQRT3, lower = 0;
     double hs = h_io, Sw = 0, Sv = 0;
+    const int wshift = __clz(cnt) - 1;                                  // cnt < 2^(32 - clz) => cnt << wshift < 2^31
+    const float wscale = __int_as_float((127 + wshift) << 23);          // 2^wshift
+    const double wunscale = __longlong_as_double((long long)(1023 - wshift) << 52);
     int it = 0;
     bool done = false;
 
@@ -190,9 +202,18 @@ static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const 
         float w0, w1, v0, v1;
         unpack2(sw2, w0, w1);
         unpack2(sv2, v0, v1);
+#ifdef TF_FP64_LANE_SUM
         Sw = (double)w0 + (double)w1;
         Sv = (double)v0 + (double)v1;
         warp_sum2(Sw, Sv);
+#else
+        // across the lanes in fixed point: one REDUX each instead of six 64-bit shuffle steps, and
+        // the result does not depend on the order.  0 <= w <= 1 and 0 <= v < 1/16 per entry, so
+        // cnt * 2^wshift < 2^31; the resolution (2.4e-7 for 300 entries, per lane) is below the
+        // rounding of the float partial sums it converts (~1e-6 at a partial sum of ~10).
+        Sw = (double)__reduce_add_sync(FULL_MASK, __float2int_rn((w0 + w1) * wscale)) * wunscale;
+        Sv = (double)__reduce_add_sync(FULL_MASK, __float2int_rn((v0 + v1) * (16.f * wscale))) * (0.0625 * wunscale);
+#endif
         Sw = fma(22.0 * (double)einv, Sv, Sw);
         evals += cnt;
 
@@ -210,7 +231,7 @@ static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const 
         if (dev < 0.5 * TG_DESNNGB) {                                   // Newton-Raphson
             // omega = 1 + dRhodHsml * hs / (3 rho) = 22 Sv / (3 Sw)  (m, c1 and hs cancel)
             // fac = 1 - (wkNgb - 295) / (3 wkNgb omega)
-            double fac = 1 - (wkNgb - TG_DESNNGB) * Sw / (wkNgb * 22.0 * Sv);
+            double fac = 1 - (wkNgb - TG_DESNNGB) * Sw * rcp_fast(wkNgb * 22.0 * Sv);
             fac = fmin(1.24, fac);
             fac = fmax(1 / 1.24, fac);
             hs *= fac;
@@ -231,9 +252,9 @@ static __device__ __forceinline__ bool find_hsml_fast(const SweepArgs &a, const 
     h_io = (float)hs;
     if (done) {                                                         // sph.c:151-153, 202-210
         const float hf = (float)hs;
-        const double c1 = TF_KW / (double)__fmul_rn(__fmul_rn(hf, hf), hf);
+        const double c1 = TF_KW * rcp_fast((double)__fmul_rn(__fmul_rn(hf, hf), hf));
         const double rho = mpart * c1 * Sw;
-        const double drho = -mpart * c1 * (3.0 * Sw - 22.0 * Sv) / hs;
+        const double drho = -mpart * c1 * (3.0 * Sw - 22.0 * Sv) * rcp_fast(hs);
         rho_out = (float)rho;
         drho_out = (float)drho;
         const float w0 = (float)c1;                                     // sph_kernel_WC6(0, hsml)
@@ -258,14 +279,7 @@ static __device__ __forceinline__ void tf_phase1_words(const float *__restrict__
     const f32x2 ib2 = pack2(ibox, ibox), mg2 = pack2(12582912.f, 12582912.f);
     const f32x2 nb2 = pack2(-box, -box);
     const int rend = min(4 * q1, nruns);     // runs [4 q0, rend)
-    int first = s_run[4 * q0];               // multiple of 8: 32-byte aligned rows
-    // same address in every lane: broadcast loads of whole rows
-    u256 X = ldg256(sx + first), Y = ldg256(sy + first), Z = ldg256(sz + first);
-    unsigned word = 0;
-#pragma unroll 1
-    for (int r = 4 * q0; r < rend; r++) {
-        const int nfirst = s_run[min(r + 1, rend - 1)];       // (past the end: re-read, unused)
-        const u256 Xn = ldg256(sx + nfirst), Yn = ldg256(sy + nfirst), Zn = ldg256(sz + nfirst);
+    auto test_run = [&](const u256 &X, const u256 &Y, const u256 &Z) -> unsigned {
         unsigned sub = 0;
         auto test2 = [&](f32x2 A, f32x2 B, f32x2 C, unsigned b0, unsigned b1) {
             f32x2 dx = sub2(xi2, A), dy = sub2(yi2, B), dz = sub2(zi2, C);
@@ -283,13 +297,31 @@ static __device__ __forceinline__ void tf_phase1_words(const float *__restrict__
         test2(X.b, Y.b, Z.b, 4u, 8u);
         test2(X.c, Y.c, Z.c, 16u, 32u);
         test2(X.d, Y.d, Z.d, 64u, 128u);
-        word |= sub << (8 * (r & 3));        // the pad of a short last run is far away
-        if ((r & 3) == 3 || r == rend - 1) {
+        return sub;                          // the pad of a short last run is far away
+    };
+    // same address in every lane: broadcast loads of whole rows (a run starts at a multiple of
+    // 8, so the rows are 32-byte aligned).  Two runs per trip on two row sets A and B that take
+    // turns, so that the hand-over of the rows in flight costs no register moves.
+    int r = 4 * q0;
+    int f = s_run[r];
+    u256 AX = ldg256(sx + f), AY = ldg256(sy + f), AZ = ldg256(sz + f);
+    unsigned word = 0;
+#pragma unroll 1
+    for (; r + 1 < rend; r += 2) {           // r is even
+        f = s_run[r + 1];
+        const u256 BX = ldg256(sx + f), BY = ldg256(sy + f), BZ = ldg256(sz + f);
+        const int sh = 8 * (r & 3);          // 0 or 16
+        word |= test_run(AX, AY, AZ) << sh;
+        f = s_run[min(r + 2, rend - 1)];     // (past the end: re-read, unused)
+        AX = ldg256(sx + f); AY = ldg256(sy + f); AZ = ldg256(sz + f);
+        word |= test_run(BX, BY, BZ) << (sh + 8);
+        if (r & 2) {                         // runs 4q .. 4q + 3 done
             gmask_lane[(r >> 2) * 32] = word;
             word = 0;
         }
-        X = Xn; Y = Yn; Z = Zn;
     }
+    if (r < rend) word |= test_run(AX, AY, AZ) << (8 * (r & 3));       // odd number of runs
+    if (rend & 3) gmask_lane[((rend - 1) >> 2) * 32] = word;            // the short last word
 }
 
 template <int MODE>
@@ -717,8 +749,8 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     sx2 = fma2(f2, ex2, sx2);
                     sy2 = fma2(f2, ey2, sy2);
                     sz2 = fma2(f2, ez2, sz2);
-                    if (use0 && fminf(u0, 1.f) < 1.f) npair++;
-                    if (use1 && fminf(u1, 1.f) < 1.f) npair++;
+                    // pairs with r < h_ij (wvt_relax.c:160): exactly those with a weight (t = 0 at u = 1)
+                    npair += (use0 && f0 != 0.f) + (use1 && f1 != 0.f);
                 }
             };
             if (PAIRS) {
