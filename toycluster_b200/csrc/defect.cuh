@@ -51,6 +51,7 @@ struct DefectTab {
     float4 *nodes;       // (centre, size) per path level, terminated by size == 0
     int *dmap;           // [n] path offset of a flagged particle
     float *pwp;          // the pair-interleaved copy of pw (tile_fast.cuh): flagged there as well
+    unsigned char *boxflag;  // [n / 32 + 1] level-0 boxes (32 particles) that hold a flagged particle
     int cap_events, cap_nodes;
 };
 
@@ -168,6 +169,7 @@ static __device__ void df_emit_path(int k, int n, float4 *__restrict__ pw, doubl
     float *w2 = d.pwp + 8 * (size_t)(k >> 1) + (k & 1) + 6;
     *w2 = __int_as_float(__float_as_int(*w2) | 0x80000000);
 #endif
+    d.boxflag[k >> 5] = 1;
     atomicAdd(&d.counts[3], 1);
 }
 

@@ -410,9 +410,11 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     const int nent = cd & 0xfff, nruns = (cd >> 12) & 0xffff;
                     const int *ent = a.tile_groups + (size_t)tl * TL_ENT;
                     int base = 0;
+                    bool anyflag = false;          // a candidate box with a particle under a displaced node
                     for (int e0 = 0; e0 < nent; e0 += 32) {
                         const int e = e0 + lane;
                         const int v = e < nent ? ent[e] : 0;
+                        if (e < nent) anyflag |= a.boxflag[v >> 4] != 0;
                         const int c = __popc(v & 0xf);
                         int incl = c;
 #pragma unroll
@@ -428,6 +430,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     // pad to a whole word of four runs (the expansion reads them four at a time)
                     const int ngp = (nruns + 3) >> 2;
                     if (lane < 4 && base + lane < 4 * ngp) s_run[base + lane] = 0;
+                    if (__any_sync(FULL_MASK, anyflag)) cd |= 1 << 28;
                 }
             }
             if (lane == 0) { ctl[C_TILE] = tl; ctl[C_CODE] = cd; ctl[C_P1NEXT] = 0; ctl[C_P1DONE] = 0; ctl[C_TNEXT] = 0; }
@@ -444,6 +447,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
         const int nruns = (code >> 12) & 0xffff;
         const int ng = (nruns + 3) >> 2;           // bit-matrix words
         const bool interior = (code >> 30) & 1;
+        const bool tile_flags = (code >> 28) & 1;
 
         // ---- phase 1: lane = target, superset bit matrix at radius R_i (tile.cuh) --------
         {
@@ -664,10 +668,16 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
             // instruction for both (each half an ordinary IEEE operation, f32x2.cuh).
             const f32x2 xi2 = pack2(pi.x, pi.x), yi2 = pack2(pi.y, pi.y), zi2 = pack2(pi.z, pi.z);
             f32x2 sx2 = pack2(0.f, 0.f), sy2 = sx2, sz2 = sx2;
-            auto batch2 = [&](const int k, const int pidx, const ulonglong2 A, const ulonglong2 B) {
+            // INTERIOR_ / FLAGS_: tile-uniform facts the loop is compiled for -- no target of the tile
+            // can see a periodic image (98.7 % of the tiles of the merger); some candidate box of the
+            // tile holds a particle underneath a displaced node (~0.1 %: defect.cuh's box flags, read
+            // by the builder).  The common instance has neither the wrap nor the flag handling.
+            auto batch2 = [&](auto interior_tag, auto flags_tag, const int k, const int pidx, const ulonglong2 A,
+                              const ulonglong2 B) {
+                constexpr bool INTERIOR_ = decltype(interior_tag)::value, FLAGS_ = decltype(flags_tag)::value;
                 f32x2 dx2 = sub2(xi2, A.x), dy2 = sub2(yi2, A.y), dz2 = sub2(zi2, B.x);
                 f32x2 ex2 = dx2, ey2 = dy2, ez2 = dz2;    // accurate separations (wrap_sep): r, direction
-                if (!interior) {
+                if (!INTERIOR_) {
                     // closest image for the PREDICATE: d - Boxsize * rint(d / Boxsize) -- one rounded
                     // subtraction, the value of tree.c:70-78 up to its sign; rint can only differ from
                     // the reference's compare for |d| within 1e-7 of Boxsize/2, which is no hit for
@@ -696,10 +706,10 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 unpack2(B.y, w0, w1);
                 float r20 = __fadd_rn(__fadd_rn(px0, py0), pz0), r21 = __fadd_rn(__fadd_rn(px1, py1), pz1);
                 const bool live = k < nU;
-                const bool fl0 = df_flagged(w0), fl1 = df_flagged(w1);
+                const bool fl0 = FLAGS_ && df_flagged(w0), fl1 = FLAGS_ && df_flagged(w1);
                 r20 = (live && !fl0) ? r20 : 3.0e38f;       // dead: the pad, hits of the second pass;
                 r21 = (live && !fl1) ? r21 : 3.0e38f;       // (the pad of an odd n is finite and far away)
-                if (__any_sync(FULL_MASK, live && (fl0 | fl1))) {       // rare: remember them for the second pass
+                if (FLAGS_ && __any_sync(FULL_MASK, live && (fl0 | fl1))) {   // rare: remember them for the second pass
                     const unsigned m0 = __ballot_sync(FULL_MASK, live && fl0), m1 = __ballot_sync(FULL_MASK, live && fl1);
                     const int p0 = nflag + __popc(m0 & lt), p1 = nflag + __popc(m0) + __popc(m1 & lt);
                     if (live && fl0 && p0 < TF_FLAG_CAP) fl[p0] = 2 * pidx;
@@ -710,10 +720,10 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 const bool inA1 = r21 < hA2, inB1 = r21 < hB2, inW1 = r21 < hsw2;
                 // r = sqrt(r2): MUFU.RSQ and one Newton step
                 float a20 = r20, a21 = r21;               // r^2 for the VALUE of r
-                if (!interior) unpack2(fma2(ez2, ez2, fma2(ey2, ey2, mul2(ex2, ex2))), a20, a21);
+                if (!INTERIOR_) unpack2(fma2(ez2, ez2, fma2(ey2, ey2, mul2(ex2, ex2))), a20, a21);
                 const float y0 = rsqrt_approx(fmaxf(a20, 1e-35f)), y1 = rsqrt_approx(fmaxf(a21, 1e-35f));
                 f32x2 r2v = pack2(r20, r21);
-                if (!interior) r2v = fma2(ez2, ez2, fma2(ey2, ey2, mul2(ex2, ex2)));
+                if (!INTERIOR_) r2v = fma2(ez2, ez2, fma2(ey2, ey2, mul2(ex2, ex2)));
                 const f32x2 y2 = pack2(y0, y1);
                 f32x2 rr = mul2(r2v, y2);
                 rr = fma2(mul2(y2, pack2(0.5f, 0.5f)), fma2(sub2(pack2(0.f, 0.f), rr), rr, r2v), rr);
@@ -758,16 +768,21 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 // per trip, so the hand-over needs no register moves)
                 const u256 *pp = (const u256 *)a.pwp;    // one 32-byte record per pair
                 const int kend = nU + lane;
-                for (int k = lane; k < kend; k += 64) {
-                    const int k1 = k + 32 < kend ? k + 32 : k;       // (past the end: re-read, unused)
-                    const int g1 = ul[k1];
-                    const u256 P1 = ldg256(pp + g1);
-                    batch2(k, g0, make_ulonglong2(P0.a, P0.b), make_ulonglong2(P0.c, P0.d));
-                    const int k2 = k + 64 < kend ? k + 64 : k;
-                    g0 = ul[k2];
-                    P0 = ldg256(pp + g0);
-                    if (k + 32 < kend) batch2(k + 32, g1, make_ulonglong2(P1.a, P1.b), make_ulonglong2(P1.c, P1.d));
-                }
+                auto pair_loop = [&](auto it, auto ft) {
+                    for (int k = lane; k < kend; k += 64) {
+                        const int k1 = k + 32 < kend ? k + 32 : k;       // (past the end: re-read, unused)
+                        const int g1 = ul[k1];
+                        const u256 P1 = ldg256(pp + g1);
+                        batch2(it, ft, k, g0, make_ulonglong2(P0.a, P0.b), make_ulonglong2(P0.c, P0.d));
+                        const int k2 = k + 64 < kend ? k + 64 : k;
+                        g0 = ul[k2];
+                        P0 = ldg256(pp + g0);
+                        if (k + 32 < kend) batch2(it, ft, k + 32, g1, make_ulonglong2(P1.a, P1.b), make_ulonglong2(P1.c, P1.d));
+                    }
+                };
+                if (!interior) pair_loop(std::false_type{}, std::true_type{});
+                else if (tile_flags) pair_loop(std::true_type{}, std::true_type{});
+                else pair_loop(std::true_type{}, std::false_type{});
                 float a0, a1;
                 unpack2(sx2, a0, a1); sx = a0 + a1;
                 unpack2(sy2, a0, a1); sy = a0 + a1;

@@ -265,7 +265,7 @@ extern "C" int tg_destroy(tg_ctx *c)
                     c->hsml_out, c->rho, c->varh, c->delta, c->bfld, c->bvh_mem, c->sub_mem, c->cpl,
                     c->ev_level, c->ev_count, c->ev_start, c->guess, c->halos, c->partial, c->scal,
                     c->flags, c->counters, c->gscratch, c->tile_ng, c->tile_groups, c->worklist,
-                    c->defect.events, c->defect.big, c->defect.counts, c->defect.nodes, c->defect.dmap};
+                    c->defect.events, c->defect.big, c->defect.counts, c->defect.nodes, c->defect.dmap, c->defect.boxflag};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : {(void *)c->rawP, (void *)c->rawS, (void *)c->outP, (void *)c->outS}) if (p) cudaFree(p);
     for (void *h : c->pinned) cudaHostUnregister(h);
@@ -451,6 +451,8 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     CUC(dmalloc(&c->defect.nodes, c->defect.cap_nodes));
     CUC(dmalloc(&c->defect.dmap, n));
     c->defect.pwp = c->pwp;
+    CUC(dmalloc(&c->defect.boxflag, (size_t)n / 32 + 1));
+    CUC(cudaMemsetAsync(c->defect.boxflag, 0, (size_t)n / 32 + 1, c->stream));
     CUC(cudaMemsetAsync(c->defect.counts, 0, 8 * sizeof(int), c->stream));
 
     CUC(dmalloc(&c->halos, MAX_HALOS));
@@ -943,6 +945,7 @@ static int prepare_index(tg_ctx *c)
         LAUNCH_CHECK();
     }
     CU(cudaMemsetAsync(c->defect.counts, 0, 8 * sizeof(int), ds));
+    CU(cudaMemsetAsync(c->defect.boxflag, 0, (size_t)n / 32 + 1, ds));
     if (emulate) {
         k_defect_detect<<<cdiv(n, T), T, 0, ds>>>(n, c->pw, c->box.box_d, c->cpl, c->defect);
         LAUNCH_CHECK();
@@ -1029,6 +1032,7 @@ static SweepArgs sweep_args(tg_ctx *c, double step)
     a.tile_mask = c->tile_mask;
     a.dmap = c->defect.dmap;
     a.dnodes = c->defect.nodes;
+    a.boxflag = c->defect.boxflag;
     return a;
 }
 
