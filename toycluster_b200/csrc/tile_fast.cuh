@@ -544,7 +544,8 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                     }
                 }
                 // pad the last batch with the target itself (its pair), marked dead by the loop below
-                if (nU + lane < ((nU + 31) & ~31)) ul[nU + lane] = PAIRS ? i >> 1 : i;
+                if (nU + lane < ((nU + 31) & ~31))
+                    ul[nU + lane] = PAIRS ? (interior ? (int)((((size_t)n + 7) & ~(size_t)7) >> 1) : i >> 1) : i;
             }
             __syncwarp();
             // the gather of the first batch starts now, ahead of the per-target constants
@@ -705,7 +706,10 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 unpack2(mul2(dz2, dz2), pz0, pz1);
                 unpack2(B.y, w0, w1);
                 float r20 = __fadd_rn(__fadd_rn(px0, py0), pz0), r21 = __fadd_rn(__fadd_rn(px1, py1), pz1);
-                const bool live = k < nU;
+                // the pad of the last batch: in an interior tile it is the ghost pair behind the last
+                // real one (finite, far away: fails every radius by itself, weight 0); elsewhere the
+                // target's own pair, which has to be masked (a far-away pad could wrap into reach)
+                const bool live = INTERIOR_ || k < nU;
                 const bool fl0 = FLAGS_ && df_flagged(w0), fl1 = FLAGS_ && df_flagged(w1);
                 r20 = (live && !fl0) ? r20 : 3.0e38f;       // dead: the pad, hits of the second pass;
                 r21 = (live && !fl1) ? r21 : 3.0e38f;       // (the pad of an odd n is finite and far away)

@@ -392,7 +392,12 @@ extern "C" int tg_create(tg_ctx **out, const tg_config *cfg)
     c->ntiles = cdiv(n, RS_TILE);
     CUC(dmalloc(&c->hist, (size_t)RS_BINS * c->ntiles + RS_BINS));   // + digit totals
     CUC(dmalloc(&c->pw, ((size_t)n + 7) & ~(size_t)7));
-    CUC(dmalloc(&c->pwp, 4 * (((size_t)n + 7) & ~(size_t)7)));
+    CUC(dmalloc(&c->pwp, 4 * (((size_t)n + 7) & ~(size_t)7) + 8));       // + the ghost pair (tile_fast.cuh)
+    {   // ghost pair: finite and far away, h = 0; written once, k_reorder_model stops before it
+        const float ghost[8] = {1e18f, 1e18f, 1e18f, 1e18f, 1e18f, 1e18f, 0.f, 0.f};
+        CUC(cudaMemcpyAsync(c->pwp + 4 * (((size_t)n + 7) & ~(size_t)7), ghost, sizeof ghost, cudaMemcpyHostToDevice, c->stream));
+        CUC(cudaStreamSynchronize(c->stream));
+    }
     CUC(dmalloc(&c->soa, 3 * (((size_t)n + 7) & ~(size_t)7)));
     CUC(dmalloc(&c->hsml_in, n));
     CUC(dmalloc(&c->rho_model, n));
