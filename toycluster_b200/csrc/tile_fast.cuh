@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 }
                 // pad the last batch with the target itself (its pair), marked dead by the loop below
                 if (nU + lane < ((nU + 31) & ~31))
-                    ul[nU + lane] = PAIRS ? (interior ? (int)((((size_t)n + 7) & ~(size_t)7) >> 1) : i >> 1) : i;
+                    ul[nU + lane] = PAIRS ? (interior && !tile_flags ? (int)((((size_t)n + 7) & ~(size_t)7) >> 1) : i >> 1) : i;
             }
             __syncwarp();
             // the gather of the first batch starts now, ahead of the per-target constants
@@ -784,9 +784,10 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                         if (k + 32 < kend) batch2(it, ft, k + 32, g1, make_ulonglong2(P1.a, P1.b), make_ulonglong2(P1.c, P1.d));
                     }
                 };
-                if (!interior) pair_loop(std::false_type{}, std::true_type{});
-                else if (tile_flags) pair_loop(std::true_type{}, std::true_type{});
-                else pair_loop(std::true_type{}, std::false_type{});
+                // two instances only (code size: the kernel's instruction fetch stalls grew with a third):
+                // the common one, and the general one, whose wrap is exact arithmetic with k = 0 inside
+                if (interior && !tile_flags) pair_loop(std::true_type{}, std::false_type{});
+                else pair_loop(std::false_type{}, std::true_type{});
                 float a0, a1;
                 unpack2(sx2, a0, a1); sx = a0 + a1;
                 unpack2(sy2, a0, a1); sy = a0 + a1;
