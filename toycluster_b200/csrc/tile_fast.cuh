@@ -473,7 +473,14 @@ __global__ void __launch_bounds__(TF_WARPS * 32, TF_BLOCKS) k_sweep_tile_fast(co
                 const int q1 = min(q0 + TF_P1_CHUNK, ng);
                 if (interior) tf_phase1_words<true>(a.soa, a.soa + n8, a.soa + 2 * n8, s_run, q0, q1, nruns, xi2, yi2, zi2, R2p, box, gmask + lane);
                 else tf_phase1_words<false>(a.soa, a.soa + n8, a.soa + 2 * n8, s_run, q0, q1, nruns, xi2, yi2, zi2, R2p, box, gmask + lane);
+                // the words went to GLOBAL memory and are read back (through L2, __ldcg) by the other
+                // warps of THIS block only: a block-scope fence before the block-scope signal is what
+                // the memory model asks for (a device-scope fence here costs 0.5 ms per step at 10 M)
+#ifdef TF_GPU_FENCE
+                __threadfence();
+#else
                 __threadfence_block();
+#endif
                 __syncwarp();
                 if (lane == 0) atomicAdd(&ctl[C_P1DONE], q1 - q0);
             }
