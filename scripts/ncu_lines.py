@@ -35,7 +35,7 @@ src = {}
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:topn]:
     f, ln = k
     if f not in src:
-        try: src[f] = open("/root/repo/gpurun_out/r02r_" + f if f == "tile_fast.cuh" else "/root/repo/toycluster_b200/csrc/" + f).read().splitlines()
+        try: src[f] = open("/root/repo/gpurun_out/r02s_" + f if f == "tile_fast.cuh" else "/root/repo/toycluster_b200/csrc/" + f).read().splitlines()
         except Exception: src[f] = []
     text = src[f][ln - 1].strip()[:90] if 0 < ln <= len(src[f]) else ""
     print(f"{f:12s}:{ln:4d} inst {v[0]/tot*100:5.1f}%  lanes {v[1]/max(v[0],1):4.1f}  samples {v[2]/ts*100:5.1f}% | {text}")
