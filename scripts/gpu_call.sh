@@ -1,3 +1,5 @@
-set -x
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 20 --warmup 5 --full-relaxation > gpurun_out/b_final3_8gpu.json 2> gpurun_out/b_final3_8gpu.err; cut -c1-200 gpurun_out/b_final3_8gpu.json; tail -2 gpurun_out/b_final3_8gpu.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 4 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/b_final3_4gpu.json 2> gpurun_out/b_final3_4gpu.err; cut -c1-200 gpurun_out/b_final3_4gpu.json
+for s in 1 7; do
+timeout 200 python scripts/fuzz_fast.py 35 400003 $s > gpurun_out/ff_new_$s.log 2>&1
+TOYGPU_LIB=$PWD/toycluster_b200/variants/libtoygpu_a_fp64sum.so timeout 200 python scripts/fuzz_fast.py 35 400003 $s > gpurun_out/ff_old_$s.log 2>&1
+done
+grep -h "within\|shift=1" gpurun_out/ff_new_1.log gpurun_out/ff_old_1.log gpurun_out/ff_new_7.log gpurun_out/ff_old_7.log | cut -c1-175
