@@ -59,10 +59,12 @@
 #define TL_BLOCKS 3                      // resident blocks per SM the kernel is compiled for
 #endif
 #ifndef TL_ENT
-#define TL_ENT 256                       // candidate level-0 boxes per tile (global list entries)
+#define TL_ENT 320                       // candidate level-0 boxes per tile (global list entries)
 #endif
 #ifndef TL_RUNS
-#define TL_RUNS 512                      // candidate runs of 8 particles per tile
+#define TL_RUNS 768                      // candidate runs of 8 particles per tile (a multiple of 128).  512 sent 0.3 %
+                                         // of the merger's tiles -- 521 to 813 runs -- to the generic sweep, 0.8 ms of
+                                         // its latency-bound tail per step at 10 M; 768 keeps four fifths of them
 #endif
 #ifndef TL_CAP
 #define TL_CAP 704                       // hits within R_i / density list entries per target
@@ -123,7 +125,7 @@ static __device__ __forceinline__ float tile_radius(float hA, float hw_raw, floa
 // tests are independent loads instead of one dependent chain per visited node -- the
 // depth-first version spent ~300 serialised L2 round trips per tile (5.2 ms per step at 10 M).
 #define TW_WARPS 8
-#define TW_QCAP 320                      // accepted nodes per level a tile may have (TL_ENT + slack)
+#define TW_QCAP (TL_ENT + 64)            // accepted nodes per level a tile may have (TL_ENT + slack)
 
 __global__ void __launch_bounds__(TW_WARPS * 32)
 k_tile_walk(Bvh t, Box bx, const float4 *__restrict__ pw, const float *__restrict__ hsml_in,

@@ -62,7 +62,7 @@
 // hits within R_i / density list entries per target (a multiple of 64; < NGBMAX, so the list cut
 // of tree.c:91-92 cannot bite).  With the bit matrix out of shared memory the lists are what is left.
 #ifndef TF_CAP
-#define TF_CAP 832
+#define TF_CAP 768
 #endif
 #ifndef TF_P1_CHUNK
 #define TF_P1_CHUNK 4
