@@ -1,4 +1,2 @@
-set -x
-timeout 2400 python -m pytest tests -q -m gpu > gpurun_out/t_all12.log 2>&1; echo "rc=$?" >> gpurun_out/t_all12.log
-grep -E "FAILED|ERROR|passed|failed|rc=|^E  " gpurun_out/t_all12.log | tail -10
-timeout 900 python bench.py --steps 20 --warmup 5 --full-relaxation > gpurun_out/b_final5_1gpu.json 2> gpurun_out/b_final5_1gpu.err; cut -c1-200 gpurun_out/b_final5_1gpu.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_r02u.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02u_ncu_list.log 2>&1
+timeout 600 python scripts/bench_configs.py r02d > gpurun_out/configs_r02d.log 2>&1; tail -1 gpurun_out/configs_r02d.log | cut -c1-200
