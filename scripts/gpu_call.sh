@@ -1,2 +1,2 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_r02u.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02u_ncu_list.log 2>&1
-timeout 600 python scripts/bench_configs.py r02d > gpurun_out/configs_r02d.log 2>&1; tail -1 gpurun_out/configs_r02d.log | cut -c1-200
+timeout 600 python -m pytest tests/test_gpu_multi.py -q -m gpu > gpurun_out/t_multi4.log 2>&1; echo "rc=$?" >> gpurun_out/t_multi4.log
+grep -E "FAILED|ERROR|passed|failed|rc=|^E  " gpurun_out/t_multi4.log | tail -5

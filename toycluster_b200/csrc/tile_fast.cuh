@@ -53,14 +53,17 @@
 #endif
 
 // Tiles in flight per block.  The bit matrix of a tile lives in a block-private stretch of
-// global memory (L2 resident: 16 KB per tile), so that TF_NB of them cost no shared memory and
+// global memory (L2 resident: TL_WORDS x 32 words = 24 KB per tile), so that TF_NB of them cost no
+// shared memory and
 // the warps of a block need no common barrier: a warp that finds no target left in tile t goes
 // on to the run list / phase 1 / targets of tile t+1 while the others finish (see the kernel).
 #ifndef TF_NB
 #define TF_NB 2
 #endif
 // hits within R_i / density list entries per target (a multiple of 64; < NGBMAX, so the list cut
-// of tree.c:91-92 cannot bite).  With the bit matrix out of shared memory the lists are what is left.
+// of tree.c:91-92 cannot bite).  With the bit matrix out of shared memory the lists and the run lists
+// (TF_NB x TL_RUNS ints) are what is left: 7 blocks x 31.6 KB fill the SM, so 768 runs per tile cost 64
+// of the 832 list entries that fitted beside 512.
 #ifndef TF_CAP
 #define TF_CAP 768
 #endif
