@@ -52,7 +52,7 @@ static __device__ __forceinline__ float global_density_model(float xf, float yf,
 {
     const double x = xf, y = yf, z = zf;
     double rho = 0;
-    if (nhalos <= 3) {
+    if (nhalos <= 1) {
         for (int i = 0; i < nhalos; i++) {
             const Halo h = halos[i];
             if (h.mass_gas == 0) continue;                   // wvt_relax.c:237
@@ -60,9 +60,10 @@ static __device__ __forceinline__ float global_density_model(float xf, float yf,
         }
         return (float)rho;
     }
-    // Substructure runs carry ~70 rows (substructure.c:127).  The result is a maximum, so the
-    // FP64 pow is only needed for rows whose float estimate is within 1e-3 of the best
-    // estimate (the estimate is good to ~1e-5): same value, ~1 pow per particle instead of 70.
+    // Substructure runs carry ~70 rows (substructure.c:127), a merger two.  The result is a
+    // maximum, so the FP64 pow is only needed for rows whose float estimate is within 1e-3 of the
+    // best estimate (the estimate is good to ~1e-5): same value, ~1 pow per particle instead of
+    // one per row.
     const float bh = (float)boxhalf;
     float best = 0;
     for (int i = 0; i < nhalos; i++) {
