@@ -233,7 +233,9 @@ int tg_get_apot(tg_ctx *ctx, float *apot);
  * the particle the file holds at position k (what sort_particles(), positions.c:405-443, makes
  * of the records after the path; NULL = the device order itself).  tg_fill_block writes
  * n_gas * {3, 1, 1, 3, 1} floats of TG_BLOCK_{POS, RHO, HSML, BFLD, RHOMODEL} to `out`
- * (io.c:141-166: P.Pos, SphP.Rho, SphP.Hsml, SphP.Bfld, SphP.Rho_Model as float). */
+ * (io.c:141-166: P.Pos, SphP.Rho, SphP.Hsml, SphP.Bfld, SphP.Rho_Model as float).  An order is
+ * only valid for the device order it was given in: after an upload or any operator that sorts
+ * again tg_fill_block fails (TG_EINVAL) until tg_set_output_order is called again. */
 enum { TG_BLOCK_POS = 0, TG_BLOCK_RHO = 1, TG_BLOCK_HSML = 2, TG_BLOCK_BFLD = 3, TG_BLOCK_RHOMODEL = 4 };
 int tg_set_output_order(tg_ctx *ctx, const size_t *order /* [n_gas] or NULL */);
 int tg_fill_block(tg_ctx *ctx, int block, float *out);

@@ -340,3 +340,11 @@ def test_gadget_blocks_from_the_soa_state():
         g.set_output_order(bad)
     # the failed call did not disturb the state: the sorted keys are still the records' keys
     assert np.array_equal(g.download()["rho"], o["rho"])
+    # a file order refers to the device order it was given in: after another operator (a new sort)
+    # it is stale, and the writer says so instead of gathering the wrong particles
+    g.set_output_order(order)
+    g.find_sph_quantities()
+    with pytest.raises(tc.ToyGpuError, match="order changed"):
+        g.fill_block("RHO")
+    g.set_output_order(None)
+    assert np.array_equal(g.fill_block("RHO"), g.download()["rho"])

@@ -126,6 +126,7 @@ struct tg_ctx {
     unsigned long long *halo_counts = nullptr;   // tg_halo_ids
     int *out_order = nullptr;       // tg_set_output_order: file position -> current device index
     bool have_out_order = false;
+    bool out_order_stale = false;   // the device order changed (upload / new index) since tg_set_output_order
     ncclComm_t comm = nullptr;
     double *errbuf = nullptr;       // [3 * nranks] gathered (err sum, err max, stop flag)
     double *hpin = nullptr;         // page-locked host words for the per-step read-backs (truly async copies)
@@ -624,6 +625,7 @@ static int upload_common(tg_ctx *c, const float *pos, const float *hsml)
     c->any_cold = cold != 0;
     c->index_valid = false;
     c->poisoned = false;
+    if (c->have_out_order) c->out_order_stale = true;
     c->have_apot = false;
     c->have_raw = false;
     CU(cudaMemsetAsync(c->rm_state, 0, sizeof(float) * n, c->stream));
@@ -674,6 +676,7 @@ extern "C" int tg_upload_soa_slice(tg_ctx *c, const float *pos, const float *hsm
     c->any_cold = cold != 0;
     c->index_valid = false;
     c->poisoned = false;
+    if (c->have_out_order) c->out_order_stale = true;
     c->have_apot = false;
     c->have_raw = false;
     CU(cudaMemsetAsync(c->rm_state, 0, sizeof(float) * n, c->stream));
@@ -833,6 +836,7 @@ extern "C" int tg_upload(tg_ctx *c, const void *P, size_t p_stride, const void *
     c->any_cold = cold != 0;
     c->index_valid = false;
     c->poisoned = false;
+    if (c->have_out_order) c->out_order_stale = true;
     c->have_apot = with_apot;
     c->have_raw = true;
     return TG_OK;
@@ -925,6 +929,7 @@ static int prepare_index(tg_ctx *c)
     if (c->poisoned) return fail(c, TG_EINVAL, "the previous step failed half-way: upload the particles again");
     int rc = join_defects(c);            // (a previous index whose flags nobody read)
     if (rc) return rc;
+    if (c->have_out_order) c->out_order_stale = true;        // a file order refers to the order it was given in
     if ((rc = sort_keys(c))) return rc;
 
     k_reorder_model<<<c->npartial, RED_THREADS, 0, c->stream>>>(
@@ -1625,6 +1630,7 @@ extern "C" int tg_set_output_order(tg_ctx *c, const size_t *order)
 {
     if (!c) return TG_EINVAL;
     TG_GROUP0(c, tg_set_output_order(k, order));          // the state is replicated on every rank
+    c->out_order_stale = false;
     if (!order) { c->have_out_order = false; return TG_OK; }
     CU(cudaSetDevice(c->cfg.device));
     const int n = c->n;
@@ -1652,6 +1658,9 @@ extern "C" int tg_fill_block(tg_ctx *c, int block, float *out)
         return fail(c, TG_EINVAL, "tg_fill_block: bad arguments");
     TG_GROUP0(c, tg_fill_block(k, block, out));
     if (c->poisoned) return fail(c, TG_EINVAL, "tg_fill_block: the last step failed; upload again");
+    if (c->have_out_order && c->out_order_stale)
+        return fail(c, TG_EINVAL, "tg_fill_block: the device order changed since tg_set_output_order "
+                                  "(an upload or an operator ran in between); set the file order again");
     CU(cudaSetDevice(c->cfg.device));
     const int n = c->n;
     const int vals = (block == TG_BLOCK_POS || block == TG_BLOCK_BFLD) ? 3 : 1;
