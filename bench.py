@@ -382,7 +382,12 @@ def main():
     sweep_ms = sweep_ms_max / args.steps
     achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "k_sweep<density+wvt>", "achieved": achieved, "peak": peak,
+    # (the sweep's events bracket the tile walk, the tile sweep and the generic sweep of the
+    # hand-backs: the dominant kernel with its two satellites, 92 + 3 + 1 % of a step)
+    kname = {"fast": "k_sweep_tile_fast<density+wvt> (+ k_tile_walk, hand-backs on k_sweep_fast)",
+             "exact": "k_sweep_tile<density+wvt> (+ k_tile_walk, hand-backs on k_sweep)",
+             "sequential": "k_sweep_tile<density> + k_sweep<wvt_seq> (+ k_tile_walk, hand-backs)"}[mode]
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["bytes_per_launch"] if traffic else None,
                 "sweep_ms": sweep_ms, "sweep_share_of_step": sweep_ms / ms_per_step,
